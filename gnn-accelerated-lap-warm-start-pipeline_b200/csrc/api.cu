@@ -1,0 +1,542 @@
+// api.cu -- host orchestration + the C ABI of libb200lap.so (include/b200lap.h).
+//
+// Every entry point enqueues hand-written sm_100a kernels on the context's stream; nothing here
+// computes on the host.  Built by nvcc only (build.py); the same translation unit also compiles
+// against tests/emul/cuda_emul.h for the CPU-side logic tests (test infrastructure, not shipped).
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "colsweep.cuh"
+#include "frontend.cuh"
+#include "solver.cuh"
+#include "features.cuh"
+#include "mlp.cuh"
+#include "../../include/b200lap.h"
+
+using namespace b200lap;
+
+// ---------------------------------------------------------------------------------------------
+// context, errors, workspace
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(B200LAP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+}  // namespace
+
+struct b200lap_ws_block {
+    unsigned char* p;
+    size_t size, off;
+};
+typedef b200lap_ws_block WsBlock;
+
+struct b200lap_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::vector<WsBlock> blocks;
+    long long launches = 0;
+    int max_dyn_smem = 227 * 1024 - 4096;
+    int solver_threads = 0;      // option: force the solver block size (tests)
+    int force_global_state = 0;  // option: keep solver state in global memory (tests)
+    int front_rows_per_cta = 0;  // option
+    int mlp_impl = 0;            // option: 0 = default
+    std::mutex mu;
+
+    void ws_reset() {
+        for (auto& b : blocks) b.off = 0;
+    }
+    void* take(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (auto& b : blocks)
+            if (b.size - b.off >= bytes) {
+                void* r = b.p + b.off;
+                b.off += bytes;
+                return r;
+            }
+        size_t sz = bytes > ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
+        void* p = nullptr;
+        if (cudaMalloc(&p, sz) != cudaSuccess) {
+            // a smaller exact-size block may still fit
+            sz = bytes;
+            if (cudaMalloc(&p, sz) != cudaSuccess) return nullptr;
+        }
+        blocks.push_back(WsBlock{(unsigned char*)p, sz, bytes});
+        return p;
+    }
+    template <typename T> T* take_n(size_t count) { return (T*)take(count * sizeof(T)); }
+};
+
+#define TAKE(var, type, count)                                                         \
+    type* var = ctx->take_n<type>(count);                                              \
+    if (!var) return fail(-1, "device workspace allocation failed (" #var ")")
+
+namespace {
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+template <typename CT> constexpr int natural_vec() { return sizeof(CT) == 4 ? 4 : 2; }
+
+template <typename CT> bool vec_ok(const CT* C, long long inst_stride, int ld, int n) {
+    const int V = natural_vec<CT>();
+    return n % V == 0 && ld % V == 0 && inst_stride % V == 0 && ((uintptr_t)C % 16) == 0;
+}
+
+// ---- column sweeps ------------------------------------------------------------------------------
+inline int strip_rows(int n) {
+    int r = n / 64;
+    if (r < 32) r = 32;
+    if (r > 256) r = 256;
+    return r;
+}
+
+template <typename CT>
+int run_col_argmin(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int batch, int n, CT* colmin, int* colarg)
+{
+    const int rps = strip_rows(n);
+    const int S = (n + rps - 1) / rps;
+    TAKE(pval, CT, (size_t)batch * S * n);
+    TAKE(prow, int, (size_t)batch * S * n);
+    if (vec_ok(C, inst_stride, ld, n)) {
+        constexpr int V = natural_vec<CT>();
+        dim3 grid((n + kColThreads * V - 1) / (kColThreads * V), S, batch);
+        auto k = k_col_argmin_partial<CT, V>;
+        B200LAP_LAUNCH(k, grid, dim3(kColThreads), 0, ctx->stream, C, inst_stride, ld, n, rps, pval, prow);
+    } else {
+        dim3 grid((n + kColThreads - 1) / kColThreads, S, batch);
+        auto k = k_col_argmin_partial<CT, 1>;
+        B200LAP_LAUNCH(k, grid, dim3(kColThreads), 0, ctx->stream, C, inst_stride, ld, n, rps, pval, prow);
+    }
+    {
+        dim3 grid((n + 255) / 256, batch);
+        auto k = k_col_argmin_final<CT>;
+        B200LAP_LAUNCH(k, grid, dim3(256), 0, ctx->stream, (const CT*)pval, (const int*)prow, S, n, colmin, colarg);
+    }
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename CT>
+int run_min_trick(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int batch, int n, const float* u, double* v)
+{
+    const int rps = strip_rows(n);
+    const int S = (n + rps - 1) / rps;
+    TAKE(pval, double, (size_t)batch * S * n);
+    if (vec_ok(C, inst_stride, ld, n)) {
+        constexpr int V = natural_vec<CT>();
+        dim3 grid((n + kColThreads * V - 1) / (kColThreads * V), S, batch);
+        auto k = k_min_trick_partial<CT, V>;
+        B200LAP_LAUNCH(k, grid, dim3(kColThreads), 0, ctx->stream, C, inst_stride, ld, n, rps, u, pval);
+    } else {
+        dim3 grid((n + kColThreads - 1) / kColThreads, S, batch);
+        auto k = k_min_trick_partial<CT, 1>;
+        B200LAP_LAUNCH(k, grid, dim3(kColThreads), 0, ctx->stream, C, inst_stride, ld, n, rps, u, pval);
+    }
+    {
+        dim3 grid((n + 255) / 256, batch);
+        B200LAP_LAUNCH(k_min_trick_final, grid, dim3(256), 0, ctx->stream, (const double*)pval, S, n, v);
+    }
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- front end ------------------------------------------------------------------------------------
+__global__ void k_force_slow_path(FrontFlags* flags, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) flags[b].any_viol = 1;
+}
+
+template <typename CT, int VEC, int EPT>
+void launch_front(b200lap_ctx* ctx, int T, int rows_per_cta, const CT* C, long long inst_stride, int ld, int batch, int n,
+                  const double* u, const double* v, double eps, double tol, double* u_tight, int* tl, int* tc, FrontFlags* flags)
+{
+    dim3 grid((n + rows_per_cta - 1) / rows_per_cta, batch);
+    auto k = k_front_end<CT, VEC, EPT>;
+    B200LAP_LAUNCH(k, grid, dim3(T), 0, ctx->stream, C, inst_stride, ld, n, rows_per_cta, u, v, eps, tol, u_tight, tl, tc, flags);
+    ctx->launches += 1;
+}
+
+template <typename CT>
+int run_front_end(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int batch, int n, const double* u,
+                  const double* v, double eps, double* u_tight, int* tl, int* tc, FrontFlags* flags)
+{
+    const double tol = eps > 1e-9 ? eps : 1e-9;
+    CK(cudaMemsetAsync(flags, 0, sizeof(FrontFlags) * (size_t)batch, ctx->stream));
+    int R = ctx->front_rows_per_cta > 0 ? ctx->front_rows_per_cta : (n >= 1024 ? 4 : 2);
+    const bool vec = vec_ok(C, inst_stride, ld, n);
+    constexpr int V = natural_vec<CT>();
+    bool done = true;
+#define FRONT(VEC_, EPT_)                                                                                             \
+    launch_front<CT, VEC_, EPT_>(ctx, round_up((n + (EPT_) - 1) / (EPT_), 32), R, C, inst_stride, ld, batch, n, u, v, \
+                                 eps, tol, u_tight, tl, tc, flags)
+    if (vec && n <= 1024 * V) FRONT(V, V);
+    else if (vec && n <= 1024 * 2 * V) FRONT(V, 2 * V);
+    else if (vec && n <= 1024 * 4 * V) FRONT(V, 4 * V);
+    else if (n <= 1024) FRONT(1, 1);
+    else if (n <= 2048) FRONT(1, 2);
+    else if (n <= 4096) FRONT(1, 4);
+    else if (n <= 8192) FRONT(1, 8);
+    else if (n <= 16384) FRONT(1, 16);
+    else done = false;
+#undef FRONT
+    if (!done) {
+        // row too long for the register-resident sweep: the solver kernel runs the (sequential)
+        // front end itself -- still on the device
+        B200LAP_LAUNCH(k_force_slow_path, dim3((batch + 127) / 128), dim3(128), 0, ctx->stream, flags, batch);
+        ctx->launches += 1;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- solve ----------------------------------------------------------------------------------------
+template <typename CT>
+int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int batch, int n, const double* u_seed,
+              const double* v_seed, double eps, int mode, int* x, int* y, int* rc, long long* trace, double* v_out)
+{
+    if (batch <= 0) return 0;
+    if (n <= 0) return fail(-2, "n <= 0");
+    TAKE(colmin, CT, (size_t)batch * n);
+    TAKE(colarg, int, (size_t)batch * n);
+    int r = run_col_argmin(ctx, C, inst_stride, ld, batch, n, colmin, colarg);
+    if (r) return r;
+    SolveArgs<CT> a;
+    a.C = C; a.inst_stride = inst_stride; a.ld = ld; a.n = n;
+    a.u_seed = u_seed; a.v_seed = v_seed; a.eps = eps; a.mode = mode;
+    a.u_tight = nullptr; a.tight_cols = nullptr; a.tight_cnt = nullptr; a.flags = nullptr;
+    if (mode == 0) {
+        TAKE(u_tight, double, (size_t)batch * n);
+        TAKE(tl, int, (size_t)batch * n * kTightCap);
+        TAKE(tc, int, (size_t)batch * n);
+        TAKE(flags, FrontFlags, (size_t)batch);
+        r = run_front_end(ctx, C, inst_stride, ld, batch, n, u_seed, v_seed, eps, u_tight, tl, tc, flags);
+        if (r) return r;
+        a.u_tight = u_tight; a.tight_cols = tl; a.tight_cnt = tc; a.flags = flags;
+    }
+    a.colmin = colmin; a.colarg = colarg;
+    const size_t state = solver_state_bytes(n);
+    a.use_smem = (!ctx->force_global_state && state <= (size_t)ctx->max_dyn_smem) ? 1 : 0;
+    a.gws = nullptr; a.gws_stride = 0;
+    if (!a.use_smem) {
+        const size_t stride = (state + 255) & ~(size_t)255;
+        unsigned char* g = (unsigned char*)ctx->take(stride * (size_t)batch);
+        if (!g) return fail(-1, "device workspace allocation failed (solver state)");
+        a.gws = g; a.gws_stride = (long long)stride;
+    }
+    a.x = x; a.y = y; a.rc = rc; a.trace = trace; a.v_out = v_out;
+    int T = ctx->solver_threads > 0 ? ctx->solver_threads : round_up((n + 3) / 4, 32);
+    if (T > 1024) T = 1024;
+    if (T < 32) T = 32;
+    const size_t smem = a.use_smem ? state : 0;
+    auto k = k_solve<CT>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+    B200LAP_LAUNCH(k, dim3(batch), dim3(T), smem, ctx->stream, a);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_narrow(const double* __restrict__ src, long long count, float* __restrict__ dst, int* exact) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const double c = src[i];
+        const float f = (float)c;
+        dst[i] = f;
+        bad |= !((double)f == c);
+    }
+    if (bad) atomicAnd(exact, 0);
+}
+
+__global__ void k_widen_ids(const int* __restrict__ src, long long count, long long* __restrict__ dst) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[i] = (long long)src[i];
+}
+
+int run_narrow(b200lap_ctx* ctx, const double* src, long long count, float* dst, int* exact) {
+    long long blocks = (count + 1023) / 1024;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    B200LAP_LAUNCH(k_narrow, dim3((unsigned)blocks), dim3(256), 0, ctx->stream, src, count, dst, exact);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+std::mutex g_default_mu;
+b200lap_ctx* g_default = nullptr;
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* b200lap_last_error(void) { return g_err.c_str(); }
+
+int b200lap_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+    return c;
+}
+
+int b200lap_ctx_create(int device, void* stream, b200lap_ctx** out) {
+    if (!out) return fail(B200LAP_ERR_ARG, "out is null");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+        return fail(B200LAP_ERR_CUDA, "no CUDA device is visible: libb200lap has no CPU path");
+    if (device < 0 || device >= count) return fail(B200LAP_ERR_ARG, "device index out of range");
+    CK(cudaSetDevice(device));
+    b200lap_ctx* c = new (std::nothrow) b200lap_ctx();
+    if (!c) return fail(-1, "host allocation failed");
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return fail(B200LAP_ERR_CUDA, "cudaStreamCreate failed"); }
+        c->own_stream = true;
+    }
+    *out = c;
+    return 0;
+}
+
+void b200lap_ctx_destroy(b200lap_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->blocks) cudaFree(b.p);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void* b200lap_ctx_stream(b200lap_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int b200lap_ctx_sync(b200lap_ctx* ctx) {
+    if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+long long b200lap_ctx_launch_count(b200lap_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value) {
+    if (!ctx || !key) return fail(B200LAP_ERR_ARG, "null argument");
+    const std::string k(key);
+    if (k == "solver_threads") ctx->solver_threads = (int)value;
+    else if (k == "force_global_state") ctx->force_global_state = (int)value;
+    else if (k == "front_rows_per_cta") ctx->front_rows_per_cta = (int)value;
+    else if (k == "mlp_impl") ctx->mlp_impl = (int)value;
+    else return fail(B200LAP_ERR_ARG, "unknown option " + k);
+    return 0;
+}
+
+b200lap_ctx* b200lap_default_ctx(void) {
+    std::lock_guard<std::mutex> g(g_default_mu);
+    if (!g_default) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+        b200lap_ctx* c = nullptr;
+        if (b200lap_ctx_create(dev, nullptr, &c) != 0) return nullptr;
+        g_default = c;
+    }
+    return g_default;
+}
+
+int b200lap_dev_narrow(b200lap_ctx* ctx, const double* src, long long count, float* dst, int* exact) {
+    if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
+    return run_narrow(ctx, src, count, dst, exact);
+}
+
+int b200lap_dev_col_argmin(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, void* colmin, int* colarg) {
+    if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
+    if (n <= 0 || batch <= 0) return fail(B200LAP_ERR_ARG, "empty problem");
+    ctx->ws_reset();
+    const long long st = (long long)n * n;
+    return is_f64 ? run_col_argmin(ctx, (const double*)C, st, n, batch, n, (double*)colmin, colarg)
+                  : run_col_argmin(ctx, (const float*)C, st, n, batch, n, (float*)colmin, colarg);
+}
+
+int b200lap_dev_min_trick(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const float* u, double* v) {
+    if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
+    if (n <= 0 || batch <= 0) return fail(B200LAP_ERR_ARG, "empty problem");
+    ctx->ws_reset();
+    const long long st = (long long)n * n;
+    return is_f64 ? run_min_trick(ctx, (const double*)C, st, n, batch, n, u, v)
+                  : run_min_trick(ctx, (const float*)C, st, n, batch, n, u, v);
+}
+
+int b200lap_dev_solve_seeded(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const double* u_seed,
+                             const double* v_seed, double eps, int* x, int* y, int* rc, long long* trace, double* v_out) {
+    if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
+    ctx->ws_reset();
+    const long long st = (long long)n * n;
+    return is_f64 ? run_solve(ctx, (const double*)C, st, n, batch, n, u_seed, v_seed, eps, 0, x, y, rc, trace, v_out)
+                  : run_solve(ctx, (const float*)C, st, n, batch, n, u_seed, v_seed, eps, 0, x, y, rc, trace, v_out);
+}
+
+int b200lap_dev_solve_cold(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, int* x, int* y, int* rc,
+                           long long* trace, double* v_out) {
+    if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
+    ctx->ws_reset();
+    const long long st = (long long)n * n;
+    return is_f64 ? run_solve(ctx, (const double*)C, st, n, batch, n, nullptr, nullptr, 0.0, 1, x, y, rc, trace, v_out)
+                  : run_solve(ctx, (const float*)C, st, n, batch, n, nullptr, nullptr, 0.0, 1, x, y, rc, trace, v_out);
+}
+
+int b200lap_dev_front_end(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const double* u_seed,
+                          const double* v_seed, double eps, double* u_tight, int* tight_cnt, int* flags) {
+    if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
+    if (n <= 0 || batch <= 0) return fail(B200LAP_ERR_ARG, "empty problem");
+    static_assert(sizeof(FrontFlags) == 16, "flags are exported as 4 x int32");
+    ctx->ws_reset();
+    TAKE(tl, int, (size_t)batch * n * kTightCap);
+    const long long st = (long long)n * n;
+    return is_f64 ? run_front_end(ctx, (const double*)C, st, n, batch, n, u_seed, v_seed, eps, u_tight, tl, tight_cnt, (FrontFlags*)flags)
+                  : run_front_end(ctx, (const float*)C, st, n, batch, n, u_seed, v_seed, eps, u_tight, tl, tight_cnt, (FrontFlags*)flags);
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------------
+namespace {
+
+struct HostMatrix {
+    const void* dev = nullptr;   // device matrix actually used
+    int is_f64 = 0;
+};
+
+// Upload `batch` binary64 matrices and, when every entry survives the binary32 round trip,
+// switch to a binary32 device copy (half the HBM traffic for every later sweep).
+int upload_matrices(b200lap_ctx* ctx, const double* C, int batch, int n, HostMatrix* out) {
+    const size_t count = (size_t)batch * n * n;
+    TAKE(d64, double, count);
+    TAKE(d32, float, count);
+    TAKE(dflag, int, 1);
+    CK(cudaMemcpyAsync(d64, C, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int one = 1;
+    CK(cudaMemcpyAsync(dflag, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    int r = run_narrow(ctx, d64, (long long)count, d32, dflag);
+    if (r) return r;
+    int exact = 0;
+    CK(cudaMemcpyAsync(&exact, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out->is_f64 = exact ? 0 : 1;
+    out->dev = exact ? (const void*)d32 : (const void*)d64;
+    return 0;
+}
+
+int solve_host(b200lap_ctx* ctx, const double* C, int batch, int n, long long* x, long long* y, const double* u_seed,
+               const double* v_seed, double eps, int mode, int* rc_out, long long* trace_out)
+{
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    ctx->ws_reset();
+    HostMatrix M;
+    int r = upload_matrices(ctx, C, batch, n, &M);
+    if (r) return r;
+    const size_t bn = (size_t)batch * n;
+    double *du = nullptr, *dv = nullptr;
+    if (mode == 0) {
+        du = ctx->take_n<double>(bn);
+        dv = ctx->take_n<double>(bn);
+        if (!du || !dv) return fail(-1, "device workspace allocation failed (seeds)");
+        CK(cudaMemcpyAsync(du, u_seed, bn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dv, v_seed, bn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TAKE(dx, int, bn);
+    TAKE(dy, int, bn);
+    TAKE(drc, int, (size_t)batch);
+    long long* dtr = nullptr;
+    if (trace_out) {
+        dtr = ctx->take_n<long long>((size_t)batch * kTraceWords);
+        if (!dtr) return fail(-1, "device workspace allocation failed (trace)");
+    }
+    const long long st = (long long)n * n;
+    r = M.is_f64 ? run_solve(ctx, (const double*)M.dev, st, n, batch, n, du, dv, eps, mode, dx, dy, drc, dtr, nullptr)
+                 : run_solve(ctx, (const float*)M.dev, st, n, batch, n, du, dv, eps, mode, dx, dy, drc, dtr, nullptr);
+    if (r) return r;
+    std::vector<int> hx(bn), hy(bn), hrc((size_t)batch);
+    CK(cudaMemcpyAsync(hx.data(), dx, bn * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hy.data(), dy, bn * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hrc.data(), drc, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (trace_out) CK(cudaMemcpyAsync(trace_out, dtr, (size_t)batch * kTraceWords * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < batch; ++b) {
+        rc_out[b] = hrc[(size_t)b];
+        if (hrc[(size_t)b] != 0) continue;
+        for (int k = 0; k < n; ++k) {
+            x[(size_t)b * n + k] = hx[(size_t)b * n + k];
+            y[(size_t)b * n + k] = hy[(size_t)b * n + k];
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+int lapjv_seeded(const double* C, int n_rows, int n_cols, long long* x, long long* y, const double* u_seed,
+                 const double* v_seed, double eps) {
+    if (n_rows <= 0 || n_cols <= 0) return -2;
+    if (n_rows != n_cols) return -4;
+    try {
+        b200lap_ctx* ctx = b200lap_default_ctx();
+        if (!ctx) return B200LAP_ERR_CUDA;
+        int rc = 0;
+        const int r = solve_host(ctx, C, 1, n_rows, x, y, u_seed, v_seed, eps, 0, &rc, nullptr);
+        return r ? r : rc;
+    } catch (const std::bad_alloc&) {
+        return -1;
+    }
+}
+
+int b200lap_lapjv_seeded_batch(const double* C, int batch, int n, long long* x, long long* y, const double* u_seed,
+                               const double* v_seed, double eps, int* rc, long long* trace) {
+    if (batch <= 0) return 0;
+    if (n <= 0) return -2;
+    try {
+        b200lap_ctx* ctx = b200lap_default_ctx();
+        if (!ctx) return B200LAP_ERR_CUDA;
+        return solve_host(ctx, C, batch, n, x, y, u_seed, v_seed, eps, 0, rc, trace);
+    } catch (const std::bad_alloc&) {
+        return -1;
+    }
+}
+
+int b200lap_lapjv(const double* C, int n, int* x, int* y) {
+    if (n <= 0) return -2;
+    try {
+        b200lap_ctx* ctx = b200lap_default_ctx();
+        if (!ctx) return B200LAP_ERR_CUDA;
+        std::vector<long long> lx((size_t)n), ly((size_t)n);
+        int rc = 0;
+        const int r = solve_host(ctx, C, 1, n, lx.data(), ly.data(), nullptr, nullptr, 0.0, 1, &rc, nullptr);
+        if (r) return r;
+        if (rc) return rc;
+        for (int k = 0; k < n; ++k) { x[k] = (int)lx[(size_t)k]; y[k] = (int)ly[(size_t)k]; }
+        return 0;
+    } catch (const std::bad_alloc&) {
+        return -1;
+    }
+}
+
+}  // extern "C"
+
+#include "api_dense.inc"

@@ -1,0 +1,625 @@
+// solver.cuh -- the seeded Jonker-Volgenant solve as ONE persistent CTA per instance.
+//
+// Reference: LAP/_lapjv_cpp/lapjv_seeded.cpp:19-173 (lapjv_seeded) and
+// LAP/_lapjv_cpp/lapjv.cpp:8-346 (_ccrrt_dense, _carr_dense, _find_dense, _scan_dense,
+// find_path_dense, _ca_dense, lapjv_internal).  Everything after the front-end sweep
+// (frontend.cuh) and the column-argmin sweep (colsweep.cuh) runs inside k_solve: greedy
+// first-fit over the tight lists, the 1.2 n fallback test, micro-ARR, Dijkstra augmentation,
+// and -- for the fallback -- column reduction, reduction transfer, two ARR passes and
+// augmentation.  No kernel launch per Dijkstra/ARR step: a step is a coalesced gather of one
+// row of C, a warp-shuffle + shared-memory reduction, and a short serial replay.
+//
+// Bit-exactness: all arithmetic is binary64 on widened matrix entries, written with the
+// reference's association, compiled with -fmad=false.  The history-dependent order of the
+// cols[] permutation (every prefix-minimum record and every tie swaps, lapjv.cpp:153-171; hits
+// are appended in position order and the first unmatched hit ends the scan, :178-213) is
+// reproduced by flagging hits in parallel into a POSITION bitmap and replaying the flagged
+// positions serially in ascending order: a swap only moves an already-visited, unflagged column
+// to an already-visited position, so pending flags stay valid.
+//
+// State (per instance): v,d binary64[n]; pred,cols,pos,y,x,free_rows int32[n]; bitmap n/32
+// words.  It lives in shared memory when 40 n + n/8 bytes fit (n <= ~5600), else in a
+// global-memory workspace that stays L2-resident.
+#pragma once
+#include "common.cuh"
+#include "frontend.cuh"
+
+namespace b200lap {
+
+constexpr int kTraceWords = 12;
+enum TraceSlot {
+    TR_PROJ = 0, TR_TIGHT = 1, TR_GREEDY = 2, TR_FALLBACK = 3, TR_MICRO = 4, TR_FREE_CR = 5,
+    TR_ARR = 6, TR_PATHS = 7, TR_COLLECT = 8, TR_RELAX = 9, TR_RC = 10, TR_SPARE = 11
+};
+
+struct SolverShared {
+    BlockRed red;
+    BlockRed2 red2;
+    int s_cnt;
+    int s_list[kTightCap];
+    int hi, final_j, next_row, aux;
+    int minw[3], maxw[3];   // hit-word ranges, rotated over 3 steps (reset one step after use)
+    unsigned int cursor, deferred;
+    long long tr[kTraceWords];
+};
+
+template <typename CT> struct SolveArgs {
+    const CT* C;
+    long long inst_stride;
+    int ld, n;
+    const double* u_seed;   // [B][n]
+    const double* v_seed;   // [B][n]
+    double eps;
+    int mode;               // 0 = seeded (lapjv_seeded), 1 = cold (lapjv_internal only)
+    const double* u_tight;  // [B][n]        (front-end sweep)
+    int* tight_cols;        // [B][n][kTightCap]
+    int* tight_cnt;         // [B][n]
+    const FrontFlags* flags;// [B]
+    const CT* colmin;       // [B][n]        (column-argmin sweep)
+    const int* colarg;      // [B][n]
+    unsigned char* gws;     // global state workspace, `gws_stride` bytes per instance (or null)
+    long long gws_stride;
+    int use_smem;
+    int* x;                 // [B][n] out
+    int* y;                 // [B][n] out
+    int* rc;                // [B] out
+    long long* trace;       // [B][kTraceWords] out (nullable)
+    double* v_out;          // [B][n] final column potentials (nullable)
+};
+
+__host__ __device__ inline size_t solver_state_bytes(int n) {
+    const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
+    return n8 * 8 * 2 + n8 * 4 * 6 + (((size_t)n + 31) / 32 + 4) * 4;
+}
+
+template <typename CT> struct SolverCtx {
+    const CT* C;
+    int ld, n;
+    double *v, *d;
+    int *pred, *cols, *pos, *y, *x, *free_rows;
+    unsigned int* bitmap;
+    SolverShared* sh;
+    Red R;
+    int step;   // relax/collect step counter (selects the minw/maxw slot)
+};
+
+// ---- serial replay of flagged positions (warp 0) ------------------------------------------------
+// mode 0: level collect (_find_dense): every flagged position is a prefix-minimum record or tie.
+// mode 1: relax (_scan_dense): every flagged position reached the level; the first unmatched
+//         one ends the path search.
+template <typename CT>
+__device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo, int whi)
+{
+    // executed by warp 0 only
+    const int lane = lane_id();
+    int hi = lo;
+    double level = INFINITY;
+    for (int w0 = wlo; w0 <= whi; w0 += 32) {
+        unsigned int bits = 0;
+        if (w0 + lane <= whi) { bits = S.bitmap[w0 + lane]; S.bitmap[w0 + lane] = 0u; }
+        unsigned int nz = __ballot_sync(kFull, bits != 0u);
+        while (nz) {
+            const int l = __ffs((int)nz) - 1;
+            nz &= nz - 1;
+            unsigned int word = __shfl_sync(kFull, bits, l);
+            if (lane == 0) {
+                while (word) {
+                    const int bpos = __ffs((int)word) - 1;
+                    word &= word - 1;
+                    const int k = (w0 + l) * 32 + bpos;
+                    const int j = S.cols[k];
+                    const double dj = S.d[j];
+                    if (dj < level) { hi = lo; level = dj; }
+                    const int c2 = S.cols[hi];
+                    S.cols[k] = c2; S.pos[c2] = k;
+                    S.cols[hi] = j; S.pos[j] = hi;
+                    ++hi;
+                }
+            }
+        }
+    }
+    hi = __shfl_sync(kFull, hi, 0);
+    if (hi == lo) hi = lo + 1;   // only reachable with NaN distances; keep moving
+    __syncwarp();
+    // unmatched column among the collected level: the LAST one in position order wins (lapjv.cpp:250-255)
+    int best = -1;
+    for (int k = lo + lane; k < hi; k += 32)
+        if (S.y[S.cols[k]] < 0) best = k;
+    best = warp_max_i(best);
+    if (lane == 0) {
+        S.sh->hi = hi;
+        S.sh->final_j = best >= 0 ? S.cols[best] : -1;
+    }
+}
+
+template <typename CT>
+__device__ __forceinline__ void replay_relax(SolverCtx<CT>& S, int hi_in, int wlo, int whi)
+{
+    const int lane = lane_id();
+    int hi = hi_in, fin = -1;
+    for (int w0 = wlo; w0 <= whi; w0 += 32) {
+        unsigned int bits = 0;
+        if (w0 + lane <= whi) { bits = S.bitmap[w0 + lane]; S.bitmap[w0 + lane] = 0u; }
+        unsigned int nz = __ballot_sync(kFull, bits != 0u);
+        while (nz) {
+            const int l = __ffs((int)nz) - 1;
+            nz &= nz - 1;
+            unsigned int word = __shfl_sync(kFull, bits, l);
+            if (lane == 0 && fin < 0) {
+                while (word) {
+                    const int bpos = __ffs((int)word) - 1;
+                    word &= word - 1;
+                    const int k = (w0 + l) * 32 + bpos;
+                    const int j = S.cols[k];
+                    if (S.y[j] < 0) { fin = j; break; }
+                    const int c2 = S.cols[hi];
+                    S.cols[k] = c2; S.pos[c2] = k;
+                    S.cols[hi] = j; S.pos[j] = hi;
+                    ++hi;
+                }
+            }
+        }
+    }
+    if (lane == 0) { S.sh->hi = hi; S.sh->final_j = fin; }
+}
+
+// ---- one shortest augmenting path (find_path_dense) ---------------------------------------------
+template <typename CT>
+__device__ int shortest_path(SolverCtx<CT>& S, int start_i)
+{
+    const int n = S.n, T = blockDim.x, tid = threadIdx.x;
+    SolverShared* sh = S.sh;
+    const CT* row0 = S.C + (size_t)start_i * S.ld;
+    for (int j = tid; j < n; j += T) {
+        S.cols[j] = j;
+        S.pos[j] = j;
+        S.pred[j] = start_i;
+        S.d[j] = (double)row0[j] - S.v[j];
+    }
+    __syncthreads();
+    int lo = 0, hi = 0, n_ready = 0, final_j = -1;
+    while (final_j < 0) {
+        if (lo == hi) {
+            // ---- level collect: positions [lo, n) in blocked ownership, prefix-min records flagged
+            n_ready = lo;
+            const int L = n - lo;
+            const int chunk = (L + T - 1) / T;
+            const int k0 = lo + tid * chunk;
+            const int k1 = min(n, k0 + chunk);
+            double lm = INFINITY;
+            for (int k = k0; k < k1; ++k) { const double t = S.d[S.cols[k]]; lm = t < lm ? t : lm; }
+            double incl = lm;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double t = __shfl_up_sync(kFull, incl, o);
+                if (lane_id() >= o) incl = t < incl ? t : incl;
+            }
+            double before = __shfl_up_sync(kFull, incl, 1);
+            if (lane_id() == 0) before = INFINITY;
+            const int p = S.R.flip();
+            if (lane_id() == 31) S.R.r->d[p][warp_id()] = incl;
+            __syncthreads();
+            {
+                const double t = lane_id() < warp_id() ? S.R.r->d[p][lane_id()] : INFINITY;
+                const double wmin = warp_min_d(t);
+                before = wmin < before ? wmin : before;
+            }
+            const int sp = S.step % 3;
+            int wmin_i = 0x7fffffff, wmax_i = -1;
+            double run = before;
+            for (int k = k0; k < k1; ++k) {
+                const double dj = S.d[S.cols[k]];
+                if (dj <= run) {
+                    atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
+                    wmin_i = min(wmin_i, k >> 5);
+                    wmax_i = max(wmax_i, k >> 5);
+                    run = dj;
+                }
+            }
+            if (wmax_i >= 0) { atomicMin(&sh->minw[sp], wmin_i); atomicMax(&sh->maxw[sp], wmax_i); }
+            __syncthreads();
+            if (warp_id() == 0) {
+                int wlo = sh->minw[sp], whi = sh->maxw[sp];
+                if (lane_id() == 0) {
+                    const int old_slot = (sp + 2) % 3;
+                    sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1;
+                    sh->tr[TR_COLLECT]++;
+                }
+                if (whi < 0) { wlo = lo >> 5; whi = wlo; }
+                replay_collect(S, lo, wlo, whi);
+            }
+            __syncthreads();
+            S.step++;
+            hi = sh->hi;
+            final_j = sh->final_j;
+        }
+        // ---- relax from every SCAN column in turn (_scan_dense)
+        while (final_j < 0 && lo != hi) {
+            const int js = S.cols[lo];
+            const int i = S.y[js];
+            const double level = S.d[js];
+            ++lo;
+            const CT* crow = S.C + (size_t)i * S.ld;
+            const double slack = ((double)crow[js] - S.v[js]) - level;
+            const int sp = S.step % 3;
+            int wmin_i = 0x7fffffff, wmax_i = -1;
+            for (int j = tid; j < n; j += T) {
+                const int k = S.pos[j];
+                if (k >= hi) {
+                    const double cand = ((double)crow[j] - S.v[j]) - slack;
+                    if (cand < S.d[j]) {
+                        S.d[j] = cand;
+                        S.pred[j] = i;
+                        if (cand == level) {
+                            atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
+                            wmin_i = min(wmin_i, k >> 5);
+                            wmax_i = max(wmax_i, k >> 5);
+                        }
+                    }
+                }
+            }
+            if (wmax_i >= 0) { atomicMin(&sh->minw[sp], wmin_i); atomicMax(&sh->maxw[sp], wmax_i); }
+            __syncthreads();
+            S.step++;
+            const int whi = sh->maxw[sp];
+            if (tid == 0) {
+                // the slot used one step ago has been read by everyone (they all passed this barrier);
+                // it is next written two steps from now, after another barrier
+                const int old_slot = (sp + 2) % 3;
+                sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1;
+                sh->tr[TR_RELAX]++;
+            }
+            if (whi >= 0) {
+                if (warp_id() == 0) {
+                    const int wlo = sh->minw[sp];
+                    replay_relax(S, hi, wlo, whi);
+                }
+                __syncthreads();
+                hi = sh->hi;
+                final_j = sh->final_j;
+            }
+        }
+    }
+    // ---- dual update of the READY columns (lapjv.cpp:270-276); lo of the caller == n_ready
+    const double level = S.d[S.cols[n_ready]];
+    for (int j = tid; j < n; j += T)
+        if (S.pos[j] < n_ready) S.v[j] += S.d[j] - level;
+    return final_j;
+}
+
+template <typename CT>
+__device__ void augment_all(SolverCtx<CT>& S, int n_free)
+{
+    for (int f = 0; f < n_free; ++f) {
+        const int root = S.free_rows[f];
+        int col = shortest_path(S, root);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            S.sh->tr[TR_PATHS]++;
+            int r;
+            do {
+                r = S.pred[col];
+                S.y[col] = r;
+                const int prev = S.x[r];
+                S.x[r] = col;
+                col = prev;
+            } while (r != root);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- ascending list of rows with x[i] < 0 (warp 0, ballot compaction) -> count -------------------
+template <typename CT>
+__device__ int collect_free_rows(SolverCtx<CT>& S)
+{
+    __syncthreads();
+    if (warp_id() == 0) {
+        int cnt = 0;
+        for (int i0 = 0; i0 < S.n; i0 += 32) {
+            const int i = i0 + lane_id();
+            const bool is_free = i < S.n && S.x[i] < 0;
+            const unsigned int m = __ballot_sync(kFull, is_free);
+            if (is_free) S.free_rows[cnt + __popc(m & ((1u << lane_id()) - 1u))] = i;
+            cnt += __popc(m);
+        }
+        if (lane_id() == 0) S.sh->aux = cnt;
+    }
+    __syncthreads();
+    return S.sh->aux;
+}
+
+// ---- cold solve: column reduction + reduction transfer (_ccrrt_dense) ----------------------------
+template <typename CT>
+__device__ int col_reduce(SolverCtx<CT>& S, const CT* colmin, const int* colarg)
+{
+    const int n = S.n, T = blockDim.x, tid = threadIdx.x;
+    int* cnt = S.pred;   // scratch: how many columns chose each row
+    for (int j = tid; j < n; j += T) {
+        const double cm = (double)colmin[j];
+        const bool hit = cm < B200LAP_LARGE;
+        S.v[j] = hit ? cm : B200LAP_LARGE;
+        S.y[j] = hit ? colarg[j] : 0;
+        S.x[j] = -1;
+        cnt[j] = 0;
+    }
+    __syncthreads();
+    // reverse column sweep == every row keeps its HIGHEST column; rows chosen twice are not unique
+    for (int j = tid; j < n; j += T) {
+        const int i = S.y[j];
+        atomicMax(&S.x[i], j);
+        atomicAdd(&cnt[i], 1);
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += T)
+        if (S.x[S.y[j]] != j) S.y[j] = -1;
+    const int n_free = collect_free_rows(S);
+    // reduction transfer, rows ascending, sequential through v (lapjv.cpp:52-68)
+    for (int i = 0; i < n; ++i) {
+        const int own = S.x[i];
+        if (own < 0 || cnt[i] != 1) continue;     // uniform: shared state read after a barrier
+        const CT* crow = S.C + (size_t)i * S.ld;
+        double m = B200LAP_LARGE;
+        for (int j = tid; j < n; j += T) {
+            if (j == own) continue;
+            const double red = (double)crow[j] - S.v[j];
+            m = red < m ? red : m;
+        }
+        m = red_min_d(S.R, m);
+        if (tid == 0) S.v[own] -= m;
+        __syncthreads();
+    }
+    return n_free;
+}
+
+// ---- cold solve: one augmenting-row-reduction pass (_carr_dense) -----------------------------------
+template <typename CT>
+__device__ int arr_pass(SolverCtx<CT>& S, int n_free)
+{
+    const int n = S.n, T = blockDim.x, tid = threadIdx.x;
+    SolverShared* sh = S.sh;
+    unsigned int cursor = 0, steps = 0;
+    int deferred = 0;
+    __syncthreads();
+    while (cursor < (unsigned int)n_free) {
+        ++steps;
+        const int r = S.free_rows[cursor++];
+        const CT* crow = S.C + (size_t)r * S.ld;
+        const double c0 = (double)crow[0] - S.v[0];
+        Top2 t;
+        top2_init(t);
+        int k1, k2;
+        double b1, b2;
+        if (c0 < B200LAP_LARGE) {
+            // lexicographic top-2 of {(c_0,0)} U {(c_j,j): c_j < LARGE}   
+            if (tid == 0) top2_push(t, c0, 0);
+            for (int j = tid; j < n; j += T) {
+                if (j == 0) continue;
+                const double red = (double)crow[j] - S.v[j];
+                if (red < B200LAP_LARGE) top2_push(t, red, j);
+            }
+            t = block_top2(S.R, t);
+        } else {
+            // entries before the first j >= 1 below LARGE are skipped, then no filter at all
+            int f = 0x7fffffff;
+            for (int j = tid; j < n; j += T) {
+                if (j == 0) continue;
+                if ((double)crow[j] - S.v[j] < B200LAP_LARGE) { f = j; break; }
+            }
+            f = red_min_i(S.R, f);
+            if (f != 0x7fffffff) {
+                if (tid == 0) top2_push(t, c0, 0);
+                for (int j = tid; j < n; j += T) {
+                    if (j < f) continue;
+                    top2_push(t, (double)crow[j] - S.v[j], j);
+                }
+            } else if (tid == 0) {
+                top2_push(t, c0, 0);
+            }
+            t = block_top2(S.R, t);
+        }
+        k1 = t.i1; b1 = t.a1;
+        if (t.i2 == 0x7fffffff) { k2 = -1; b2 = B200LAP_LARGE; } else { k2 = t.i2; b2 = t.a2; }
+        if (tid == 0) {
+            sh->tr[TR_ARR]++;
+            int owner = S.y[k1];
+            const double lowered = S.v[k1] - (b2 - b1);
+            const bool does_lower = lowered < S.v[k1];
+            if (steps < cursor * (unsigned int)n) {
+                if (does_lower) {
+                    S.v[k1] = lowered;
+                } else if (owner >= 0 && k2 >= 0) {
+                    k1 = k2;
+                    owner = S.y[k2];
+                }
+                if (owner >= 0) {
+                    if (does_lower) S.free_rows[--cursor] = owner;
+                    else S.free_rows[deferred++] = owner;
+                }
+            } else if (owner >= 0) {
+                S.free_rows[deferred++] = owner;
+            }
+            S.x[r] = k1;
+            S.y[k1] = r;
+            sh->cursor = cursor;
+            sh->deferred = (unsigned int)deferred;
+        }
+        __syncthreads();
+        cursor = sh->cursor;
+        deferred = (int)sh->deferred;
+    }
+    return deferred;
+}
+
+template <typename CT>
+__device__ void cold_solve(SolverCtx<CT>& S, const CT* colmin, const int* colarg)
+{
+    int left = col_reduce(S, colmin, colarg);
+    if (threadIdx.x == 0) S.sh->tr[TR_FREE_CR] = left;
+    for (int pass = 0; left > 0 && pass < 2; ++pass) left = arr_pass(S, left);
+    __syncthreads();
+    if (left > 0) augment_all(S, left);
+}
+
+// ---- the persistent per-instance kernel -----------------------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(1024, 1) k_solve(SolveArgs<CT> a)
+{
+    B200LAP_DYN_SMEM(dyn);
+    __shared__ SolverShared sh;
+    const int b = blockIdx.x, n = a.n, T = blockDim.x, tid = threadIdx.x;
+    SolverCtx<CT> S;
+    S.C = a.C + (size_t)b * a.inst_stride;
+    S.ld = a.ld;
+    S.n = n;
+    {
+        unsigned char* base = a.use_smem ? dyn : a.gws + (size_t)b * a.gws_stride;
+        const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
+        S.v = (double*)base; base += n8 * 8;
+        S.d = (double*)base; base += n8 * 8;
+        S.pred = (int*)base; base += n8 * 4;
+        S.cols = (int*)base; base += n8 * 4;
+        S.pos = (int*)base; base += n8 * 4;
+        S.y = (int*)base; base += n8 * 4;
+        S.x = (int*)base; base += n8 * 4;
+        S.free_rows = (int*)base; base += n8 * 4;
+        S.bitmap = (unsigned int*)base;
+    }
+    S.sh = &sh;
+    S.R.r = &sh.red;
+    S.R.r2 = &sh.red2;
+    S.R.par = 0;
+    S.step = 0;
+    if (tid == 0) {
+        sh.s_cnt = 0;
+        sh.minw[0] = sh.minw[1] = sh.minw[2] = 0x7fffffff;
+        sh.maxw[0] = sh.maxw[1] = sh.maxw[2] = -1;
+        for (int q = 0; q < kTraceWords; ++q) sh.tr[q] = 0;
+    }
+    for (int w = tid; w < (n + 31) / 32 + 4; w += T) S.bitmap[w] = 0u;
+    const CT* colmin = a.colmin + (size_t)b * n;
+    const int* colarg = a.colarg + (size_t)b * n;
+    int rc = 0;
+    __syncthreads();
+
+    if (a.mode == 1) {
+        cold_solve(S, colmin, colarg);
+    } else {
+        const double eps = a.eps;
+        const double tol = eps > 1e-9 ? eps : 1e-9;
+        const double* us = a.u_seed + (size_t)b * n;
+        const double* vs = a.v_seed + (size_t)b * n;
+        int* tl = a.tight_cols + (size_t)b * n * kTightCap;
+        int* tc = a.tight_cnt + (size_t)b * n;
+        double* u = S.d;   // row potentials live in d[] until the first path search
+        const FrontFlags fl = a.flags[b];
+        unsigned long long tight = fl.total_tight;
+        int infeasible = fl.infeasible;
+        for (int j = tid; j < n; j += T) { S.v[j] = vs[j]; S.x[j] = -1; S.y[j] = -1; }
+        if (!fl.any_viol) {
+            const double* ut = a.u_tight + (size_t)b * n;
+            for (int j = tid; j < n; j += T) u[j] = ut[j];
+            __syncthreads();
+        } else {
+            // projection fired somewhere: redo the whole front end in reference order
+            __syncthreads();
+            long long fired = 0;
+            for (int i = 0; i < n; ++i) {
+                double ui = us[i];
+                fired += project_row(S.C + (size_t)i * S.ld, n, S.v, ui, eps, S.R);
+                if (tid == 0) u[i] = ui;
+            }
+            __syncthreads();
+            tight = 0;
+            infeasible = 0;
+            for (int i = 0; i < n; ++i) {
+                double ut;
+                int cnt;
+                front_row_generic(S.C + (size_t)i * S.ld, n, S.v, u[i], eps, tol, S.R, &sh.s_cnt, sh.s_list,
+                                  tl + (size_t)i * kTightCap, &ut, &cnt, &infeasible);
+                if (tid == 0) { u[i] = ut; tc[i] = cnt; }
+                tight += (unsigned long long)cnt;
+            }
+            if (tid == 0) sh.tr[TR_PROJ] = fired;
+            __threadfence_block();
+            __syncthreads();
+        }
+        if (infeasible) {
+            rc = -3;
+        } else {
+            // ---- greedy first-fit over the tight lists (lapjv_seeded.cpp:76-93)
+            int i = 0;
+            while (i < n) {
+                if (tid == 0) {
+                    int matched = 0;
+                    for (; i < n; ++i) {
+                        const int c = tc[i];
+                        if (c > kTightCap) break;          // list truncated: cooperative rescan below
+                        const int* li = tl + (size_t)i * kTightCap;
+                        for (int q = 0; q < c; ++q) {
+                            const int j = li[q];
+                            if (S.y[j] < 0) { S.x[i] = j; S.y[j] = i; ++matched; break; }
+                        }
+                    }
+                    sh.next_row = i;
+                    sh.tr[TR_GREEDY] += matched;
+                }
+                __syncthreads();
+                i = sh.next_row;
+                if (i < n) {
+                    const CT* crow = S.C + (size_t)i * S.ld;
+                    const double ui = u[i];
+                    int first = 0x7fffffff;
+                    for (int j = tid; j < n; j += T) {
+                        if (S.y[j] >= 0) continue;
+                        if (fabs(((double)crow[j] - ui) - S.v[j]) <= tol) { first = j; break; }
+                    }
+                    first = red_min_i(S.R, first);
+                    if (tid == 0 && first != 0x7fffffff) { S.x[i] = first; S.y[first] = i; sh.tr[TR_GREEDY]++; }
+                    ++i;
+                    __syncthreads();
+                }
+            }
+            const int n_free = collect_free_rows(S);
+            if (tid == 0) sh.tr[TR_TIGHT] = (long long)tight;
+            if ((double)(long long)tight < 1.2 * n) {
+                if (tid == 0) sh.tr[TR_FALLBACK] = 1;
+                __syncthreads();
+                cold_solve(S, colmin, colarg);
+            } else if (n_free > 0) {
+                // ---- micro-ARR (lapjv_seeded.cpp:136-159); "j1 in free_cols" == y[j1] < 0 after greedy
+                for (int f = 0; f < n_free; ++f) {
+                    const int r = S.free_rows[f];
+                    const CT* crow = S.C + (size_t)r * S.ld;
+                    const double ur = u[r];
+                    Top2 t;
+                    top2_init(t);
+                    for (int j = tid; j < n; j += T) top2_push(t, ((double)crow[j] - ur) - S.v[j], j);
+                    t = block_top2(S.R, t);
+                    if (tid == 0 && t.i1 != 0x7fffffff && t.a2 - t.a1 > tol && S.y[t.i1] < 0) {
+                        S.v[t.i1] += t.a2 - t.a1;
+                        sh.tr[TR_MICRO]++;
+                    }
+                    __syncthreads();
+                }
+                augment_all(S, n_free);
+            }
+        }
+    }
+    __syncthreads();
+    if (rc == 0) {
+        for (int j = tid; j < n; j += T) {
+            a.x[(size_t)b * n + j] = S.x[j];
+            a.y[(size_t)b * n + j] = S.y[j];
+            if (a.v_out) a.v_out[(size_t)b * n + j] = S.v[j];
+        }
+    }
+    if (tid == 0) {
+        a.rc[b] = rc;
+        sh.tr[TR_RC] = rc;
+        if (a.trace)
+            for (int q = 0; q < kTraceWords; ++q) a.trace[(size_t)b * kTraceWords + q] = sh.tr[q];
+    }
+}
+
+}  // namespace b200lap

@@ -1,0 +1,134 @@
+/* b200lap.h -- C ABI of libb200lap.so, the B200 (sm_100a) implementation of the warm-start LAP
+ * hot path of egbariajad/GNN-Accelerated-LAP-Warm-Start-Pipeline.
+ *
+ * Plain pointers and sizes only (no torch types).  Every entry point names the reference
+ * interface it replaces (paths relative to the reference repository root).  Unless stated
+ * otherwise a function returns 0 on success, a negative reference return code where the
+ * reference defines one (-1 allocation, -2 n <= 0, -3 infeasible, -4 not square), or
+ * B200LAP_ERR_CUDA (-100) / B200LAP_ERR_UNSUPPORTED (-101) / B200LAP_ERR_ARG (-102);
+ * b200lap_last_error() then describes the failure.  There is no CPU fallback: without a
+ * usable CUDA device every compute entry point fails with B200LAP_ERR_CUDA.
+ */
+#ifndef B200LAP_H
+#define B200LAP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200LAP_ERR_CUDA (-100)
+#define B200LAP_ERR_UNSUPPORTED (-101)
+#define B200LAP_ERR_ARG (-102)
+
+#define B200LAP_ROW_FEAT_DIM 21   /* gnn/features.py:223-241 */
+#define B200LAP_TRACE_WORDS 12
+#define B200LAP_TOPK_MAX 32
+
+typedef struct b200lap_ctx b200lap_ctx;       /* one per (device, stream): workspaces + stream */
+typedef struct b200lap_model b200lap_model;   /* OneGNN weights packed on a device              */
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Drop-in: the reference's only extern "C" symbol.
+ *    Replaces LAP/lap/lapjv_seeded.h:8-13 (definition LAP/_lapjv_cpp/lapjv_seeded.cpp:19-23),
+ *    bound by LAP/lap/_seeded_jv.pyx:7-12.  HOST pointers, borrowed for the call; C row-major
+ *    n_rows x n_cols binary64; x[n_rows], y[n_cols] written only on success.
+ * ------------------------------------------------------------------------------------------ */
+int lapjv_seeded(const double* C, int n_rows, int n_cols, long long* x, long long* y,
+                 const double* u_seed, const double* v_seed, double eps);
+
+/* Cold solve = lapjv_internal (LAP/_lapjv_cpp/lapjv.cpp:323-346, C++ linkage in the reference,
+ * reached through LAP/_lapjv_cpp/_lapjv.pyx:38-129).  HOST pointers, square n x n. */
+int b200lap_lapjv(const double* C, int n, int* x, int* y);
+
+/* Batched host entry: `batch` independent instances, C [batch][n][n], seeds [batch][n].
+ * rc[batch] receives each instance's lapjv_seeded return code; trace (nullable)
+ * [batch][B200LAP_TRACE_WORDS] the phase counters (proj_triggers, tight_edges, greedy_matched,
+ * took_fallback, micro_bumps, free_after_cr, arr_iters, aug_paths, collect_calls, relax_cols, rc, -). */
+int b200lap_lapjv_seeded_batch(const double* C, int batch, int n, long long* x, long long* y,
+                               const double* u_seed, const double* v_seed, double eps, int* rc,
+                               long long* trace);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Contexts (device-pointer API).  A context owns a stream and cached workspaces on one
+ *    device; calls on one context are serialised by the caller.  `stream` may be 0 (the
+ *    context then creates its own non-blocking stream) or an existing cudaStream_t.
+ * ------------------------------------------------------------------------------------------ */
+int b200lap_ctx_create(int device, void* stream, b200lap_ctx** out);
+void b200lap_ctx_destroy(b200lap_ctx* ctx);
+void* b200lap_ctx_stream(b200lap_ctx* ctx);          /* the cudaStream_t work is enqueued on */
+int b200lap_ctx_sync(b200lap_ctx* ctx);
+int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value);
+long long b200lap_ctx_launch_count(b200lap_ctx* ctx); /* kernels launched so far on this context */
+const char* b200lap_last_error(void);
+int b200lap_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Dense half on DEVICE buffers.  `C` points to `batch` row-major n x n matrices, instance
+ *    stride n*n elements, stored as binary32 (is_f64 = 0; the caller guarantees every entry is
+ *    exactly representable) or binary64 (is_f64 = 1).  All outputs are device buffers.
+ * ------------------------------------------------------------------------------------------ */
+/* binary64 -> binary32 copy; *exact (device int, set to 1 by the caller) is cleared when any entry
+ * does not survive the round trip. */
+int b200lap_dev_narrow(b200lap_ctx* ctx, const double* src, long long count, float* dst, int* exact);
+/* column minima + first row attaining them (gnn/features.py:218 col_min; lapjv.cpp:21-32). colmin has C's type. */
+int b200lap_dev_col_argmin(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, void* colmin, int* colarg);
+/* gnn/features.py:161-243 compute_row_features -> feat [batch][n][21] f32; topv [batch][n][topk] the
+ * topk smallest entries of every row, ascending, rounded to binary32 (feeds gnn/one_gnn.py:143-147). */
+int b200lap_dev_row_features(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, int topk,
+                             const void* colmin, float* feat, float* topv);
+/* gnn/one_gnn.py:89-120 OneGNN.forward (inference, all-true mask) from features + top-k values
+ * -> u [batch][n] f32 (mean-centred) and raw [batch][n] f32 (head output before centring, nullable). */
+int b200lap_dev_onegnn_forward(b200lap_ctx* ctx, const b200lap_model* model, const float* feat, const float* topv,
+                               int has_cost, int batch, int n, float* u, float* raw);
+/* scripts/gnn_benchmark.py:262 min-trick: v_j = min_i (C_ij - (double)u_i), binary64, exact. */
+int b200lap_dev_min_trick(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const float* u, double* v);
+/* GNNPredictor.predict (scripts/gnn_benchmark.py:213-289): features -> OneGNN -> min-trick.
+ * u64/v64 [batch][n] binary64 (u64 holds the binary32 values widened); feat/topv nullable. */
+int b200lap_dev_predict_duals(b200lap_ctx* ctx, const b200lap_model* model, const void* C, int is_f64, int batch,
+                              int n, double* u64, double* v64, float* u32, float* feat);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. Solver half on DEVICE buffers (same matrix conventions).  x,y int32 [batch][n] (written
+ *    for instances with rc == 0), rc int32 [batch], trace int64 [batch][12] nullable,
+ *    v_out binary64 [batch][n] nullable (final column potentials).
+ * ------------------------------------------------------------------------------------------ */
+int b200lap_dev_solve_seeded(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const double* u_seed,
+                             const double* v_seed, double eps, int* x, int* y, int* rc, long long* trace,
+                             double* v_out);
+int b200lap_dev_solve_cold(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, int* x, int* y, int* rc,
+                           long long* trace, double* v_out);
+/* Front-end sweep alone (solvers/advanced_dual.py:14-63 project/reduce/check stated on the solver's
+ * own sweeps): u_tight [batch][n], tight_cnt [batch][n], flags [batch][4] int32 =
+ * {any_violation, infeasible, total_tight lo, total_tight hi}. */
+int b200lap_dev_front_end(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const double* u_seed,
+                          const double* v_seed, double eps, double* u_tight, int* tight_cnt, int* flags);
+/* features -> OneGNN -> min-trick -> seeded solve without leaving the device. */
+int b200lap_dev_pipeline(b200lap_ctx* ctx, const b200lap_model* model, const void* C, int is_f64, int batch, int n,
+                         double eps, int* x, int* y, int* rc, double* u64, double* v64, long long* trace);
+
+/* ------------------------------------------------------------------------------------------
+ * 5. Model weights.  `params` is one HOST binary32 blob holding the reference state_dict tensors
+ *    in the order of gnn/one_gnn.py's module definition:
+ *    input_proj.0.{weight[H,F],bias[H]}, input_proj.2.{weight,bias}[H],
+ *    per block: fc1.{weight[H,H],bias}, fc2.{weight,bias}, norm.{weight,bias};
+ *    pre_out.{weight[1,H],bias[1]}, row_out.0.{weight[H/2,H],bias}, row_out.3.{weight[1,H/2],bias[1]},
+ *    edge_mlp.0.{weight[H,1],bias[H]}, edge_mlp.2.{weight[H,H],bias[H]}, message_norm.{weight,bias}[H].
+ * ------------------------------------------------------------------------------------------ */
+int b200lap_model_create(b200lap_ctx* ctx, const float* params, long long n_params, int in_dim, int hidden,
+                         int layers, int topk, b200lap_model** out);
+void b200lap_model_destroy(b200lap_model* model);
+
+/* ------------------------------------------------------------------------------------------
+ * 6. Host-buffer conveniences used by the Python mirrors (upload, run, download).
+ * ------------------------------------------------------------------------------------------ */
+/* gnn.compute_row_features(C) -> feat[n][21] (gnn/features.py:161-243). */
+int b200lap_compute_row_features(const double* C, int n, float* feat);
+/* predict + solve for a batch of host matrices [batch][n][n]; u,v nullable outputs [batch][n]. */
+int b200lap_pipeline_batch(const b200lap_model* model, const double* C, int batch, int n, double eps,
+                           long long* x, long long* y, int* rc, double* u, double* v, long long* trace);
+b200lap_ctx* b200lap_default_ctx(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LAP_H */
