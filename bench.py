@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- LAP instances/s of the warm-start hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (N=1): BASELINE.json configs[1] -- a batch of 64 mixed-family (uniform/sparse/metric/clustered)
+n=2048 instances, random-init OneGNN (hidden 192, layers 4, k 16, torch.manual_seed(0)), synthetic data
+snapped to the binary32 grid.  One step = features -> OneGNN -> min-trick -> seeded JV over the whole
+batch.  N>1: one process per GPU (torchrun), every rank owns its own 64 instances (weak scaling, no
+data-path collective); the timed region is bracketed by barrier + synchronize, time = max over ranks.
+
+  value      device-resident throughput (C already in HBM as binary32), CUDA events on the context stream
+  e2e        the same step through the host-buffer C ABI (b200lap_pipeline_batch): pinned host float64 in,
+             host int64 assignments out, host<->device copies inside the timed region
+  roofline   dominant dense-pass kernel (k_row_features) at algorithmic bytes = one read of C = 4 n^2 B per
+             instance, timed live with CUDA events; per-kernel table in `dense_pass`
+  cpu_baseline   the oracle's CPU pipeline (NumPy features, NumPy OneGNN, reference-compiled lapjv_seeded when
+             oracle/_ref travelled, else the C port) on a bounded sample, on this box's host cores; plus SciPy.
+
+--impl reference times that CPU pipeline as the headline line instead (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "gnn-accelerated-lap-warm-start-pipeline_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+N_INST = 2048
+BATCH = 64
+FAMILIES = ("uniform", "sparse", "metric", "clustered")
+METRIC = "LAP instances/s end-to-end (features -> OneGNN -> min-trick -> lapjv_seeded), mixed-family n=2048"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def named_state_dict():
+    import torch
+    from gnn.one_gnn import OneGNN
+    torch.manual_seed(0)
+    module = OneGNN(21, hidden=192, layers=4, dropout=0.1, topk=16).eval()
+    return {k: v.detach().cpu().numpy() for k, v in module.state_dict().items()}
+
+
+def make_batch(rank: int, batch: int = BATCH, n: int = N_INST):
+    from solvers import generators as gen
+    out = np.empty((batch, n, n), dtype=np.float64)
+    fams = []
+    for k in range(batch):
+        fam = FAMILIES[k % len(FAMILIES)]
+        out[k] = gen.make_instance(fam, n, seed=42 + rank * batch + k)
+        fams.append(fam)
+    return out, fams
+
+
+# ---- CPU pipeline (the reference arm / cpu_baseline) ---------------------------------------------------
+_W = {"sd": None, "use_ref": False, "cache": {}}
+
+
+def _cpu_init(sd, use_ref):
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[var] = "1"
+    _W["sd"], _W["use_ref"] = sd, use_ref
+
+
+def _cpu_instance(key):
+    if key not in _W["cache"]:
+        from solvers import generators as gen
+        fam, n, seed = key
+        _W["cache"] = {key: gen.make_instance(fam, n, seed=seed)}
+    return _W["cache"][key]
+
+
+def _cpu_prepare(key):
+    _cpu_instance(key)
+    import oracle
+    oracle.port_lib()
+    return 0
+
+
+def _cpu_worker(key):
+    """The oracle's CPU pipeline on one instance: NumPy features (binary64) -> NumPy OneGNN (binary32) ->
+    min-trick -> lapjv_seeded (the reference's own compiled solver when oracle/_ref is present)."""
+    from oracle import pipeline_np
+    C = _cpu_instance(key)
+    t0 = time.perf_counter()
+    pipeline_np.solve(C, _W["sd"], topk=16, use_ref=_W["use_ref"])
+    return time.perf_counter() - t0
+
+
+def _scipy_worker(key):
+    from scipy.optimize import linear_sum_assignment
+    C = _cpu_instance(key)
+    t0 = time.perf_counter()
+    linear_sum_assignment(C)
+    return time.perf_counter() - t0
+
+
+def cpu_pipeline_throughput(n: int, procs: int, rounds: int = 1):
+    """One instance per worker process (families cycled), `procs` workers, 1 BLAS thread each -> instances/s."""
+    import multiprocessing as mp
+    import oracle
+    oracle.build()
+    use_ref = oracle.ref_available()
+    sd = named_state_dict()
+    keys = [(FAMILIES[k % len(FAMILIES)], n, 42 + k) for k in range(procs)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs, initializer=_cpu_init, initargs=(sd, use_ref)) as pool:
+        pool.map(_cpu_prepare, keys, chunksize=1)     # generate the instances, load the solver library (untimed)
+        walls, per = [], []
+        for _ in range(rounds):
+            t0 = time.perf_counter()
+            per += pool.map(_cpu_worker, keys, chunksize=1)
+            walls.append(time.perf_counter() - t0)
+        ts = time.perf_counter()
+        sp = pool.map(_scipy_worker, keys, chunksize=1)
+        swall = time.perf_counter() - ts
+    return {"inst_per_s": procs * rounds / sum(walls), "walls": walls, "mean_latency_s": float(np.mean(per)),
+            "kind": "reference" if use_ref else "port", "scipy_inst_per_s": len(sp) / swall,
+            "scipy_mean_latency_s": float(np.mean(sp))}
+
+
+# ---- clocks --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=3)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [nm for k, nm in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ---- the B200 arm ----------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import b200lap
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    ctx = b200lap.default_context(local)
+    model = b200lap.Model(ctx, named_state_dict(), topk=16)
+    Ch, fams = make_batch(rank)
+    n, B = N_INST, BATCH
+    Cd = torch.from_numpy(Ch.astype(np.float32)).cuda()          # exact: instances live on the binary32 grid
+    assert torch.equal(Cd.double().cpu(), torch.from_numpy(Ch)), "instances must be binary32-representable"
+    stream = ctx.torch_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # -- device-resident throughput
+    def step_resident():
+        return ctx.pipeline(model, Cd)
+
+    for _ in range(args.warmup):
+        out = step_resident()
+    ctx.sync()
+    barrier()
+    launches0 = ctx.launches
+    with ClockSampler(local) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            out = step_resident()
+        e1.record(stream)
+        ctx.sync()
+        barrier()
+        ms_resident = e0.elapsed_time(e1)
+    launches = ctx.launches - launches0
+    rc = out[2].cpu().numpy()
+    assert (rc == 0).all(), rc
+    t = torch.tensor([ms_resident], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    # -- per-kernel dense pass (CUDA events on the launching stream), same resident batch
+    u = torch.zeros((B, n), dtype=torch.float32, device="cuda")
+
+    def timed(fn, reps):
+        fn(); ctx.sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        ctx.sync()
+        return a.elapsed_time(b) / reps
+
+    reps = max(3, args.steps)
+    feat, topv = ctx.row_features(Cd, topk=16)
+    u64, v64, u32 = ctx.predict_duals(model, Cd)
+    bytes_one_read = 4.0 * n * n * B
+    dense = {}
+    for name, fn in (("col_argmin", lambda: ctx.col_argmin(Cd)),
+                     ("row_features", lambda: ctx.row_features(Cd, topk=16)),
+                     ("onegnn_mlp", lambda: ctx.onegnn_forward(model, feat, topv)),
+                     ("min_trick", lambda: ctx.min_trick(Cd, u32)),
+                     ("front_end", lambda: ctx.front_end(Cd, u64, v64)),
+                     ("predict_duals", lambda: ctx.predict_duals(model, Cd))):
+        ms = timed(fn, reps)
+        dense[name] = {"ms": round(ms, 4), "GBps_one_read_of_C": round(bytes_one_read / (ms * 1e-3) / 1e9, 1)}
+    solve_ms = timed(lambda: ctx.solve_seeded(Cd, u64, v64), max(2, args.steps // 2))
+    dense["solve_seeded"] = {"ms": round(solve_ms, 3)}
+
+    # -- the n = 16384 dense pass (config 4: 1 GiB binary32 C), the size the HBM target is quoted on
+    big = None
+    if rank == 0 and not args.skip_big:
+        try:
+            nb = 16384
+            g = torch.Generator(device="cuda").manual_seed(42)
+            Cb = torch.rand((nb, nb), generator=g, device="cuda", dtype=torch.float32)
+            fb, tb = ctx.row_features(Cb, topk=16)
+            ub64, vb64, ub32 = ctx.predict_duals(model, Cb)
+            one = 4.0 * nb * nb
+            big = {}
+            for name, fn in (("col_argmin", lambda: ctx.col_argmin(Cb)),
+                             ("row_features", lambda: ctx.row_features(Cb, topk=16)),
+                             ("onegnn_mlp", lambda: ctx.onegnn_forward(model, fb, tb)),
+                             ("min_trick", lambda: ctx.min_trick(Cb, ub32)),
+                             ("front_end", lambda: ctx.front_end(Cb, ub64, vb64)),
+                             ("predict_duals", lambda: ctx.predict_duals(model, Cb))):
+                ms = timed(fn, 5)
+                big[name] = {"ms": round(ms, 4), "GBps_one_read_of_C": round(one / (ms * 1e-3) / 1e9, 1)}
+            del Cb, fb, tb
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001
+            big = {"error": repr(exc)}
+
+    # -- end to end through the host-buffer C ABI (pinned host float64 in, host int64 out)
+    lib = ctx.lib
+    Cp = torch.from_numpy(Ch).pin_memory()
+    xh = torch.empty((B, n), dtype=torch.int64).pin_memory()
+    yh = torch.empty((B, n), dtype=torch.int64).pin_memory()
+    rch = np.zeros(B, dtype=np.int32)
+    # the host entry points use the library's default context; make it this rank's device
+    torch.cuda.set_device(local)
+    import ctypes
+    from b200lap.runtime import pack_state_dict
+    dctx = lib.b200lap_default_ctx()
+    blob, in_dim, hidden, layers = pack_state_dict(named_state_dict())
+    hmodel = ctypes.c_void_p()
+    assert lib.b200lap_model_create(dctx, blob.ctypes.data, blob.size, in_dim, hidden, layers, 16, ctypes.byref(hmodel)) == 0
+
+    def step_e2e():
+        r = lib.b200lap_pipeline_batch(hmodel, Cp.data_ptr(), B, n, 1e-12, xh.data_ptr(), yh.data_ptr(), rch.ctypes.data, None, None, None)
+        assert r == 0 and (rch == 0).all(), (r, b200lap._lib.last_error(lib))
+
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    # resident and host paths must agree bit for bit
+    assert np.array_equal(out[0].cpu().numpy().astype(np.int64), xh.numpy()), "host and resident paths disagree"
+
+    if rank == 0:
+        peak, which = load_peaks()
+        fk = dense["row_features"]
+        achieved = fk["GBps_one_read_of_C"]
+        cpu = None
+        if not args.skip_cpu:
+            procs = min(os.cpu_count() or 1, 16)
+            c = cpu_pipeline_throughput(N_INST, procs=procs)
+            cpu = {"value": round(c["inst_per_s"], 3), "unit": "instances/s", "cores": procs, "kind": c["kind"],
+                   "sample": f"{procs} mixed-family n={N_INST} instances, one per worker process, 1 thread each "
+                             f"(mean latency {c['mean_latency_s']:.2f} s)",
+                   "scipy_linear_sum_assignment": {"value": round(c["scipy_inst_per_s"], 3), "unit": "instances/s",
+                                                   "mean_latency_s": round(c["scipy_mean_latency_s"], 3)}}
+        line = {
+            "metric": METRIC, "value": round(world * B / (ms_step * 1e-3), 2), "unit": "instances/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{B} mixed-family n={N_INST} instances per GPU (BASELINE configs[1], mid2048), random-init OneGNN h192/L4/k16",
+                       "families": list(FAMILIES), "storage": "binary32 C (exact), binary64 solver arithmetic",
+                       "l2": "inputs (1.07 GB/step) larger than L2", "parallelism": f"instance-sharded x{world}"},
+            "e2e": {"value": round(world * B / e2e_s, 2), "unit": "instances/s", "h2d_bytes_per_step": int(Ch.nbytes),
+                    "d2h_bytes_per_step": int(B * n * 4 * 2 + rch.nbytes), "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "kernel": "k_row_features (21-D features + top-16, one read of C)", "achieved": achieved,
+                         "peak": peak, "peak_source": which, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None},
+            "dense_pass_n2048_b64": dense,
+            "dense_pass_n16384": big,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---- the reference arm -------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    procs = min(os.cpu_count() or 1, 16)
+    c = cpu_pipeline_throughput(N_INST, procs=procs, rounds=args.warmup + args.steps)
+    kind = c["kind"]
+    walls = c["walls"][args.warmup:]
+    v = procs * len(walls) / sum(walls)
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "instances/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(1e3 * procs / v, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{BATCH} mixed-family n={N_INST} instances per GPU (BASELINE configs[1], mid2048), random-init OneGNN h192/L4/k16",
+                       "families": list(FAMILIES)},
+            "cpu_baseline": {"value": round(v, 3), "unit": "instances/s", "cores": procs, "kind": kind,
+                             "sample": f"each step = {procs} mixed-family n={N_INST} instances over {procs} worker processes, 1 thread each"},
+            "e2e": {"value": round(v, 3), "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
+    ap.add_argument("--skip-big", action="store_true", help="omit the n=16384 dense-pass table")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        args.warmup = min(args.warmup, 1)
+        args.steps = min(args.steps, 3)
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

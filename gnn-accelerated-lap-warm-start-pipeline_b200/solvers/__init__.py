@@ -1,0 +1,4 @@
+"""``solvers`` -- the reference's solver wrappers over the B200 ``lap`` drop-in, plus the instance generators."""
+from .lap_solver import LAPSolver, SeededLAPSolver  # noqa: F401
+from .generators import (generate_uniform_costs, generate_sparse_costs, generate_metric_costs,  # noqa: F401
+                         generate_clustered_costs, make_instance, mixed_batch, snap_to_fp32_grid)

@@ -57,3 +57,21 @@ def noisy_oracle_seeds(C: np.ndarray, sigma: float, seed: int = 42):
         u = u + rs.normal(0, sigma, u.shape[0])
         v = v + rs.normal(0, sigma, v.shape[0])
     return u, v
+
+
+def feature_close(got: np.ndarray, ref: np.ndarray, rtol: float = 1e-4, atol: float = 1e-7) -> None:
+    """|got - ref| <= rtol * |ref| + atol per entry; the absolute floor covers quantities formed by
+    cancellation (positional sines at multiples of pi, zero gaps)."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    err = np.abs(got - ref)
+    lim = rtol * np.abs(ref) + atol
+    if not np.all(err <= lim):
+        bad = np.argwhere(err > lim)
+        i, j = bad[0]
+        raise AssertionError(f"{bad.shape[0]} feature entries off; first at row {i} feature {j}: got {got[i, j]!r} ref {ref[i, j]!r}")
+
+
+def state_dict_from_golden(g, prefix: str = "small_sd/") -> dict:
+    return {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)}

@@ -1,0 +1,170 @@
+"""CPU tests of the KERNEL LOGIC: the product's csrc/ sources compiled for the SIMT interpreter in
+tests/emul/ (test infrastructure; see its header) and compared with the oracle on small instances.
+This is where the bit-exact tie-breaking of the parallel replay, the host orchestration in api.cu and
+the dense kernels' arithmetic are exercised without a GPU.  The parity tests proper (`-m gpu`) run the
+nvcc-built library on the B200."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import onegnn_np, pipeline_np
+from solvers import generators as gen
+from b200lap import _lib
+from _fixtures import GOLDEN, feature_close, mintrick_seeds, noisy_oracle_seeds, dense_int, state_dict_from_golden, load_known_answers
+import _capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMUL_DIR = os.path.join(HERE, "emul")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run([os.path.join(EMUL_DIR, "build.sh")], check=True, capture_output=True)
+    lib = _lib.bind(ctypes.CDLL(os.path.join(EMUL_DIR, "libb200lap_emul.so")))
+    ctx = lib.b200lap_default_ctx()
+    assert ctx
+    return lib, ctx
+
+
+def _opt(lib, ctx, key, val):
+    assert lib.b200lap_ctx_set_option(ctx, key.encode(), val) == 0
+
+
+def _check_seeded(lib, C, u, v, tag):
+    tro = oracle.Trace()
+    try:
+        xo, yo, _ = oracle.port_lapjv_seeded(C, u, v, trace=tro)
+        rco = 0
+    except ValueError:
+        rco = -3
+    rc, x, y, tr = _capi.seeded(lib, C, u, v)
+    assert rc == rco, tag
+    if rc == 0:
+        assert np.array_equal(x, xo) and np.array_equal(y, yo), tag
+        assert not _capi.trace_matches(tro.as_dict(), tr), (tag, _capi.trace_matches(tro.as_dict(), tr))
+    else:
+        assert (x == -1).all() and (y == -1).all()
+
+
+@pytest.mark.parametrize("threads,global_state", [(32, 0), (64, 1)])
+def test_solver_matches_oracle(emu, threads, global_state):
+    lib, ctx = emu
+    _opt(lib, ctx, "solver_threads", threads)
+    _opt(lib, ctx, "force_global_state", global_state)
+    rng = np.random.default_rng(threads)
+    for fam in ("uniform", "sparse1e6", "metric", "clustered"):
+        for n in (1, 2, 5, 33, 48):
+            C = gen.make_instance(fam, n, seed=int(rng.integers(1000)))
+            rc, x, y = _capi.cold(lib, C)
+            xo, yo = oracle.port_lapjv_internal(C)
+            assert rc == 0 and np.array_equal(x, xo) and np.array_equal(y, yo), (fam, n)
+            u, v = mintrick_seeds(C, rng)
+            _check_seeded(lib, C, u, v, (fam, n, "mintrick"))
+            for sigma in (0.0, 1e-2):
+                u, v = noisy_oracle_seeds(C, sigma)
+                _check_seeded(lib, C, u, v, (fam, n, sigma))
+    _opt(lib, ctx, "solver_threads", 0)
+    _opt(lib, ctx, "force_global_state", 0)
+
+
+def test_solver_ties_and_known_answers(emu):
+    lib, ctx = emu
+    _opt(lib, ctx, "solver_threads", 32)
+    g = load_known_answers()
+    for k in range(int(g["n_small"])):
+        C = g[f"small{k}_C"]
+        if not np.isfinite(C).all():
+            continue
+        rc, x, y = _capi.cold(lib, C)
+        assert rc == 0 and list(x) == list(g[f"small{k}_x"]) and list(y) == list(g[f"small{k}_y"]), k
+    # tie-heavy integer matrices: zero seeds, min-trick seeds, noisy seeds
+    rng = np.random.default_rng(11)
+    for sz, hard in ((24, False), (40, True)):
+        C = dense_int(sz, 10, hard, seed=77 + sz).astype(np.float64)
+        _check_seeded(lib, C, np.zeros(sz), np.zeros(sz), ("int", sz, "zero"))
+        _check_seeded(lib, C, np.zeros(sz), C.min(axis=0), ("int", sz, "colmin"))
+        u, v = noisy_oracle_seeds(C, 0.0)
+        _check_seeded(lib, C, u, v, ("int", sz, "oracle"))
+        _check_seeded(lib, C, u + 1.0, v + 1.0, ("int", sz, "shifted"))
+    # the reference's own printed cases (LAP/test_seeded.py:8-12, LAP/demo_seeded.py:18-37)
+    C = np.array([[4.0, 1.0, 3.0], [2.0, 0.0, 5.0], [3.0, 2.0, 2.0]])
+    rc, x, y = _capi.seeded_dropin(lib, C, np.zeros(3), np.zeros(3))
+    assert rc == 0 and list(x) == [1, 0, 2]
+    C = np.array([[4.0, 2.0, 8.0, 6.0], [6.0, 4.0, 1.0, 2.0], [8.0, 6.0, 4.0, 3.0], [2.0, 8.0, 5.0, 7.0]])
+    rc, x, y = _capi.seeded_dropin(lib, C, np.zeros(4), np.array([2.0, 2.0, 1.0, 2.0]))
+    assert rc == 0 and list(x) == [1, 2, 3, 0] and list(y) == [3, 0, 1, 2]
+    rc, x, y = _capi.seeded_dropin(lib, C, np.full(4, 10.0), np.zeros(4))
+    assert rc == 0 and C[np.arange(4), x].sum() == 8.0
+    # guards
+    assert _capi.seeded_dropin(lib, np.zeros((2, 3)), np.zeros(2), np.zeros(3))[0] == -4
+    _opt(lib, ctx, "solver_threads", 0)
+
+
+def test_non_fp32_matrix_takes_the_binary64_path(emu):
+    lib, ctx = emu
+    rng = np.random.default_rng(5)
+    C = rng.uniform(0, 1, (37, 37))          # not on the binary32 grid
+    u, v = mintrick_seeds(C, rng)
+    _check_seeded(lib, C, u, v, "f64")
+    rc, x, y = _capi.cold(lib, C)
+    xo, yo = oracle.port_lapjv_internal(C)
+    assert rc == 0 and np.array_equal(x, xo)
+
+
+def test_dense_half_matches_golden(emu):
+    lib, ctx = emu
+    g = np.load(os.path.join(GOLDEN, "dense_golden.npz"))
+    sd = state_dict_from_golden(g)
+    model = _capi.make_model(lib, ctx, sd, 8)
+    for fam in ("uniform", "sparse1e6", "clustered", "odd", "tiny"):
+        C = g[f"{fam}/C"]
+        n = C.shape[0]
+        ref = g[f"{fam}/feat"]
+        for is64 in (0, 1):
+            Cd = np.ascontiguousarray(C, dtype=np.float64 if is64 else np.float32)
+            feat = np.zeros((n, 21), np.float32)
+            topv = np.zeros((n, 8), np.float32)
+            assert lib.b200lap_dev_row_features(ctx, Cd.ctypes.data, is64, 1, n, 8, None, feat.ctypes.data, topv.ctypes.data) == 0
+            feature_close(feat, ref, rtol=1e-5)
+            ks = min(8, n)
+            assert np.array_equal(topv[:, :ks], np.sort(C.astype(np.float32), axis=1)[:, :ks])
+        u = np.zeros(n, np.float32)
+        raw = np.zeros(n, np.float32)
+        assert lib.b200lap_dev_onegnn_forward(ctx, model, np.ascontiguousarray(ref).ctypes.data, topv.ctypes.data, 1, 1, n,
+                                              u.ctypes.data, raw.ctypes.data) == 0
+        scale = np.abs(g[f"{fam}/small_raw"]).max()
+        assert np.abs(u - g[f"{fam}/small_u"]).max() <= 1e-5 * scale
+        Cf = np.ascontiguousarray(C, dtype=np.float32)
+        v = np.zeros(n)
+        assert lib.b200lap_dev_min_trick(ctx, Cf.ctypes.data, 0, 1, n, g[f"{fam}/small_u"].ctypes.data, v.ctypes.data) == 0
+        assert np.array_equal(v, g[f"{fam}/small_v"])          # v is exact given u
+        # the whole path without leaving the "device": bit-exact assignment for the SAME (u, v)
+        u64 = np.zeros(n); v64 = np.zeros(n)
+        x = np.zeros(n, np.int32); y = np.zeros(n, np.int32); rcs = np.zeros(1, np.int32)
+        assert lib.b200lap_dev_pipeline(ctx, model, Cf.ctypes.data, 0, 1, n, 1e-12, x.ctypes.data, y.ctypes.data, rcs.ctypes.data,
+                                        u64.ctypes.data, v64.ctypes.data, None) == 0 and rcs[0] == 0
+        assert np.array_equal(v64, pipeline_np.min_trick(C, u64.astype(np.float32)))
+        xo, yo, _ = oracle.port_lapjv_seeded(C, u64, v64)
+        assert np.array_equal(x, xo) and np.array_equal(y, yo)
+    lib.b200lap_model_destroy(model)
+
+
+def test_front_end_flags(emu):
+    lib, ctx = emu
+    rng = np.random.default_rng(9)
+    n = 40
+    C = np.ascontiguousarray(gen.make_instance("uniform", n, 3), dtype=np.float32)
+    C64 = C.astype(np.float64)
+    u, v = mintrick_seeds(C64, rng)
+    ut = np.zeros(n); tc = np.zeros(n, np.int32); fl = np.zeros(4, np.int32)
+    assert lib.b200lap_dev_front_end(ctx, C.ctypes.data, 0, 1, n, u.ctypes.data, v.ctypes.data, 1e-12, ut.ctypes.data, tc.ctypes.data, fl.ctypes.data) == 0
+    rc, uo, vo, xo, yo, tr = oracle.port_front_end(C64, u, v)
+    assert fl[0] == 0 and fl[1] == 0 and np.array_equal(ut, uo) and int(fl[2]) == tr["tight_edges"] == int(tc.sum())
+    assert int(fl[2]) == pipeline_np.tight_edge_count(C64, uo, vo)
+    # infeasible seeds are reported by the sweep (and repaired later by the solver's projection)
+    assert lib.b200lap_dev_front_end(ctx, C.ctypes.data, 0, 1, n, (u + 1).ctypes.data, v.ctypes.data, 1e-12, ut.ctypes.data, tc.ctypes.data, fl.ctypes.data) == 0
+    assert fl[0] == 1 and fl[1] == 1
