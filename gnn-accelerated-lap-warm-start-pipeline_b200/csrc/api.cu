@@ -245,9 +245,18 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
     if (T > 1024) T = 1024;
     if (T < 32) T = 32;
     const size_t smem = a.use_smem ? state : 0;
-    auto k = k_solve<CT>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
-    B200LAP_LAUNCH(k, dim3(batch), dim3(T), smem, ctx->stream, a);
+    const int per_thread = (n + T - 1) / T;      // row entries a thread keeps in registers per step
+#define SOLVE(MAXC_)                                                                                                       \
+    do {                                                                                                                   \
+        auto k = k_solve<CT, MAXC_>;                                                                                       \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024))); \
+        B200LAP_LAUNCH(k, dim3(batch), dim3(T), smem, ctx->stream, a);                                                     \
+    } while (0)
+    if (per_thread <= 4) SOLVE(4);
+    else if (per_thread <= 8) SOLVE(8);
+    else if (per_thread <= 16) SOLVE(16);
+    else SOLVE(0);
+#undef SOLVE
     ctx->launches += 1;
     CK(cudaGetLastError());
     return 0;

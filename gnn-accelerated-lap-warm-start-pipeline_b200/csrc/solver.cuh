@@ -83,6 +83,31 @@ template <typename CT> struct SolverCtx {
     int step;   // relax/collect step counter (selects the minw/maxw slot)
 };
 
+// ---- one thread-strided pass over a matrix row ----------------------------------------------------
+// With MAXC > 0 (blockDim.x * MAXC >= n) the thread's entries are loaded into registers FIRST, as
+// independent coalesced loads, and only then handed to `body` -- a row costs one memory latency, not
+// one per entry (the bodies branch on shared state, which otherwise serialises the loads).
+template <int MAXC, typename CT, typename F>
+__device__ __forceinline__ void row_scan(const CT* __restrict__ crow, int n, F&& body)
+{
+    const int T = blockDim.x, tid = threadIdx.x;
+    if constexpr (MAXC > 0) {
+        CT c[MAXC];
+#pragma unroll
+        for (int q = 0; q < MAXC; ++q) {
+            const int j = tid + q * T;
+            c[q] = j < n ? __ldg(crow + j) : (CT)0;
+        }
+#pragma unroll
+        for (int q = 0; q < MAXC; ++q) {
+            const int j = tid + q * T;
+            if (j < n) body(j, (double)c[q]);
+        }
+    } else {
+        for (int j = tid; j < n; j += T) body(j, (double)crow[j]);
+    }
+}
+
 // ---- serial replay of flagged positions (warp 0) ------------------------------------------------
 // mode 0: level collect (_find_dense): every flagged position is a prefix-minimum record or tie.
 // mode 1: relax (_scan_dense): every flagged position reached the level; the first unmatched
@@ -164,18 +189,18 @@ __device__ __forceinline__ void replay_relax(SolverCtx<CT>& S, int hi_in, int wl
 }
 
 // ---- one shortest augmenting path (find_path_dense) ---------------------------------------------
-template <typename CT>
+template <int MAXC, typename CT>
 __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
 {
     const int n = S.n, T = blockDim.x, tid = threadIdx.x;
     SolverShared* sh = S.sh;
     const CT* row0 = S.C + (size_t)start_i * S.ld;
-    for (int j = tid; j < n; j += T) {
+    row_scan<MAXC>(row0, n, [&](int j, double c) {
         S.cols[j] = j;
         S.pos[j] = j;
         S.pred[j] = start_i;
-        S.d[j] = (double)row0[j] - S.v[j];
-    }
+        S.d[j] = c - S.v[j];
+    });
     __syncthreads();
     int lo = 0, hi = 0, n_ready = 0, final_j = -1;
     while (final_j < 0) {
@@ -240,13 +265,15 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
             const double level = S.d[js];
             ++lo;
             const CT* crow = S.C + (size_t)i * S.ld;
-            const double slack = ((double)crow[js] - S.v[js]) - level;
+            const CT c_js = __ldg(crow + js);        // issued together with the row loads below
+            const double v_js = S.v[js];
             const int sp = S.step % 3;
             int wmin_i = 0x7fffffff, wmax_i = -1;
-            for (int j = tid; j < n; j += T) {
+            row_scan<MAXC>(crow, n, [&](int j, double c) {
+                const double slack = ((double)c_js - v_js) - level;
                 const int k = S.pos[j];
                 if (k >= hi) {
-                    const double cand = ((double)crow[j] - S.v[j]) - slack;
+                    const double cand = (c - S.v[j]) - slack;
                     if (cand < S.d[j]) {
                         S.d[j] = cand;
                         S.pred[j] = i;
@@ -257,7 +284,7 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                         }
                     }
                 }
-            }
+            });
             if (wmax_i >= 0) { atomicMin(&sh->minw[sp], wmin_i); atomicMax(&sh->maxw[sp], wmax_i); }
             __syncthreads();
             S.step++;
@@ -287,12 +314,12 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
     return final_j;
 }
 
-template <typename CT>
+template <int MAXC, typename CT>
 __device__ void augment_all(SolverCtx<CT>& S, int n_free)
 {
     for (int f = 0; f < n_free; ++f) {
         const int root = S.free_rows[f];
-        int col = shortest_path(S, root);
+        int col = shortest_path<MAXC>(S, root);
         __syncthreads();
         if (threadIdx.x == 0) {
             S.sh->tr[TR_PATHS]++;
@@ -330,7 +357,7 @@ __device__ int collect_free_rows(SolverCtx<CT>& S)
 }
 
 // ---- cold solve: column reduction + reduction transfer (_ccrrt_dense) ----------------------------
-template <typename CT>
+template <int MAXC, typename CT>
 __device__ int col_reduce(SolverCtx<CT>& S, const CT* colmin, const int* colarg)
 {
     const int n = S.n, T = blockDim.x, tid = threadIdx.x;
@@ -360,11 +387,12 @@ __device__ int col_reduce(SolverCtx<CT>& S, const CT* colmin, const int* colarg)
         if (own < 0 || cnt[i] != 1) continue;     // uniform: shared state read after a barrier
         const CT* crow = S.C + (size_t)i * S.ld;
         double m = B200LAP_LARGE;
-        for (int j = tid; j < n; j += T) {
-            if (j == own) continue;
-            const double red = (double)crow[j] - S.v[j];
-            m = red < m ? red : m;
-        }
+        row_scan<MAXC>(crow, n, [&](int j, double c) {
+            if (j != own) {
+                const double red = c - S.v[j];
+                m = red < m ? red : m;
+            }
+        });
         m = red_min_d(S.R, m);
         if (tid == 0) S.v[own] -= m;
         __syncthreads();
@@ -373,7 +401,7 @@ __device__ int col_reduce(SolverCtx<CT>& S, const CT* colmin, const int* colarg)
 }
 
 // ---- cold solve: one augmenting-row-reduction pass (_carr_dense) -----------------------------------
-template <typename CT>
+template <int MAXC, typename CT>
 __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
 {
     const int n = S.n, T = blockDim.x, tid = threadIdx.x;
@@ -385,34 +413,33 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
         ++steps;
         const int r = S.free_rows[cursor++];
         const CT* crow = S.C + (size_t)r * S.ld;
-        const double c0 = (double)crow[0] - S.v[0];
+        const double c0 = (double)__ldg(crow) - S.v[0];
         Top2 t;
         top2_init(t);
         int k1, k2;
         double b1, b2;
+        // One pass gathers both candidate sets; which one applies depends on c_0 (uniform).
+        //   c_0 <  LARGE: lexicographic top-2 of {(c_0,0)} U {(c_j,j): j>=1, c_j < LARGE}   
+        //   c_0 >= LARGE: entries before the first j >= 1 below LARGE are skipped, then no filter at all
+        Top2 tf;            // filtered set
+        top2_init(tf);
+        int f = 0x7fffffff;
+        row_scan<MAXC>(crow, n, [&](int j, double c) {
+            if (j != 0) {
+                const double red = c - S.v[j];
+                if (red < B200LAP_LARGE) { top2_push(tf, red, j); f = min(f, j); }
+            }
+        });
         if (c0 < B200LAP_LARGE) {
-            // lexicographic top-2 of {(c_0,0)} U {(c_j,j): c_j < LARGE}   
-            if (tid == 0) top2_push(t, c0, 0);
-            for (int j = tid; j < n; j += T) {
-                if (j == 0) continue;
-                const double red = (double)crow[j] - S.v[j];
-                if (red < B200LAP_LARGE) top2_push(t, red, j);
-            }
-            t = block_top2(S.R, t);
+            if (tid == 0) top2_push(tf, c0, 0);
+            t = block_top2(S.R, tf);
         } else {
-            // entries before the first j >= 1 below LARGE are skipped, then no filter at all
-            int f = 0x7fffffff;
-            for (int j = tid; j < n; j += T) {
-                if (j == 0) continue;
-                if ((double)crow[j] - S.v[j] < B200LAP_LARGE) { f = j; break; }
-            }
             f = red_min_i(S.R, f);
             if (f != 0x7fffffff) {
                 if (tid == 0) top2_push(t, c0, 0);
-                for (int j = tid; j < n; j += T) {
-                    if (j < f) continue;
-                    top2_push(t, (double)crow[j] - S.v[j], j);
-                }
+                row_scan<MAXC>(crow, n, [&](int j, double c) {
+                    if (j >= f) top2_push(t, c - S.v[j], j);
+                });
             } else if (tid == 0) {
                 top2_push(t, c0, 0);
             }
@@ -451,18 +478,18 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
     return deferred;
 }
 
-template <typename CT>
+template <int MAXC, typename CT>
 __device__ void cold_solve(SolverCtx<CT>& S, const CT* colmin, const int* colarg)
 {
-    int left = col_reduce(S, colmin, colarg);
+    int left = col_reduce<MAXC>(S, colmin, colarg);
     if (threadIdx.x == 0) S.sh->tr[TR_FREE_CR] = left;
-    for (int pass = 0; left > 0 && pass < 2; ++pass) left = arr_pass(S, left);
+    for (int pass = 0; left > 0 && pass < 2; ++pass) left = arr_pass<MAXC>(S, left);
     __syncthreads();
-    if (left > 0) augment_all(S, left);
+    if (left > 0) augment_all<MAXC>(S, left);
 }
 
 // ---- the persistent per-instance kernel -----------------------------------------------------------
-template <typename CT>
+template <typename CT, int MAXC>
 __global__ void __launch_bounds__(1024, 1) k_solve(SolveArgs<CT> a)
 {
     B200LAP_DYN_SMEM(dyn);
@@ -503,7 +530,7 @@ __global__ void __launch_bounds__(1024, 1) k_solve(SolveArgs<CT> a)
     __syncthreads();
 
     if (a.mode == 1) {
-        cold_solve(S, colmin, colarg);
+        cold_solve<MAXC>(S, colmin, colarg);
     } else {
         const double eps = a.eps;
         const double tol = eps > 1e-9 ? eps : 1e-9;
@@ -570,10 +597,9 @@ __global__ void __launch_bounds__(1024, 1) k_solve(SolveArgs<CT> a)
                     const CT* crow = S.C + (size_t)i * S.ld;
                     const double ui = u[i];
                     int first = 0x7fffffff;
-                    for (int j = tid; j < n; j += T) {
-                        if (S.y[j] >= 0) continue;
-                        if (fabs(((double)crow[j] - ui) - S.v[j]) <= tol) { first = j; break; }
-                    }
+                    row_scan<MAXC>(crow, n, [&](int j, double c) {
+                        if (S.y[j] < 0 && fabs((c - ui) - S.v[j]) <= tol) first = min(first, j);
+                    });
                     first = red_min_i(S.R, first);
                     if (tid == 0 && first != 0x7fffffff) { S.x[i] = first; S.y[first] = i; sh.tr[TR_GREEDY]++; }
                     ++i;
@@ -585,7 +611,7 @@ __global__ void __launch_bounds__(1024, 1) k_solve(SolveArgs<CT> a)
             if ((double)(long long)tight < 1.2 * n) {
                 if (tid == 0) sh.tr[TR_FALLBACK] = 1;
                 __syncthreads();
-                cold_solve(S, colmin, colarg);
+                cold_solve<MAXC>(S, colmin, colarg);
             } else if (n_free > 0) {
                 // ---- micro-ARR (lapjv_seeded.cpp:136-159); "j1 in free_cols" == y[j1] < 0 after greedy
                 for (int f = 0; f < n_free; ++f) {
@@ -594,7 +620,7 @@ __global__ void __launch_bounds__(1024, 1) k_solve(SolveArgs<CT> a)
                     const double ur = u[r];
                     Top2 t;
                     top2_init(t);
-                    for (int j = tid; j < n; j += T) top2_push(t, ((double)crow[j] - ur) - S.v[j], j);
+                    row_scan<MAXC>(crow, n, [&](int j, double c) { top2_push(t, (c - ur) - S.v[j], j); });
                     t = block_top2(S.R, t);
                     if (tid == 0 && t.i1 != 0x7fffffff && t.a2 - t.a1 > tol && S.y[t.i1] < 0) {
                         S.v[t.i1] += t.a2 - t.a1;
@@ -602,7 +628,7 @@ __global__ void __launch_bounds__(1024, 1) k_solve(SolveArgs<CT> a)
                     }
                     __syncthreads();
                 }
-                augment_all(S, n_free);
+                augment_all<MAXC>(S, n_free);
             }
         }
     }
