@@ -164,13 +164,17 @@ __global__ void k_force_slow_path(FrontFlags* flags, int batch) {
 }
 
 template <typename CT, int VEC, int EPT>
-void launch_front(b200lap_ctx* ctx, int T, int rows_per_cta, const CT* C, long long inst_stride, int ld, int batch, int n,
+int launch_front(b200lap_ctx* ctx, int T, int rows_per_cta, const CT* C, long long inst_stride, int ld, int batch, int n,
                   const double* u, const double* v, double eps, double tol, double* u_tight, int* tl, int* tc, FrontFlags* flags)
 {
     dim3 grid((n + rows_per_cta - 1) / rows_per_cta, batch);
-    auto k = k_front_end<CT, VEC, EPT>;
-    B200LAP_LAUNCH(k, grid, dim3(T), 0, ctx->stream, C, inst_stride, ld, n, rows_per_cta, u, v, eps, tol, u_tight, tl, tc, flags);
+    constexpr bool kVsm = EPT >= 16;
+    auto k = k_front_end<CT, VEC, EPT, kVsm>;
+    const size_t smem = kVsm ? (size_t)n * sizeof(double) : 0;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200LAP_LAUNCH(k, grid, dim3(T), smem, ctx->stream, C, inst_stride, ld, n, rows_per_cta, u, v, eps, tol, u_tight, tl, tc, flags);
     ctx->launches += 1;
+    return 0;
 }
 
 template <typename CT>
@@ -179,13 +183,14 @@ int run_front_end(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, 
 {
     const double tol = eps > 1e-9 ? eps : 1e-9;
     CK(cudaMemsetAsync(flags, 0, sizeof(FrontFlags) * (size_t)batch, ctx->stream));
-    int R = ctx->front_rows_per_cta > 0 ? ctx->front_rows_per_cta : (n >= 1024 ? 4 : 2);
+    int R = ctx->front_rows_per_cta > 0 ? ctx->front_rows_per_cta : (n >= 8192 ? 16 : (n >= 1024 ? 8 : 2));
     const bool vec = vec_ok(C, inst_stride, ld, n);
     constexpr int V = natural_vec<CT>();
     bool done = true;
+    int fr = 0;
 #define FRONT(VEC_, EPT_)                                                                                             \
-    launch_front<CT, VEC_, EPT_>(ctx, round_up((n + (EPT_) - 1) / (EPT_), 32), R, C, inst_stride, ld, batch, n, u, v, \
-                                 eps, tol, u_tight, tl, tc, flags)
+    fr = launch_front<CT, VEC_, EPT_>(ctx, round_up((n + (EPT_) - 1) / (EPT_), 32), R, C, inst_stride, ld, batch, n, u, v, \
+                                      eps, tol, u_tight, tl, tc, flags)
     if (vec && n <= 1024 * V) FRONT(V, V);
     else if (vec && n <= 1024 * 2 * V) FRONT(V, 2 * V);
     else if (vec && n <= 1024 * 4 * V) FRONT(V, 4 * V);
@@ -196,6 +201,7 @@ int run_front_end(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, 
     else if (n <= 16384) FRONT(1, 16);
     else done = false;
 #undef FRONT
+    if (fr) return fr;
     if (!done) {
         // row too long for the register-resident sweep: the solver kernel runs the (sequential)
         // front end itself -- still on the device

@@ -84,7 +84,21 @@ __global__ void k_col_argmin_final(const CT* __restrict__ pval, const int* __res
     if (j >= n) return;
     CT best = (CT)INFINITY;
     int brow = -1;
-    for (int s = 0; s < S; ++s) {
+    int s = 0;
+    for (; s + 8 <= S; s += 8) {       // 16 independent loads in flight, folded in strip order
+        CT pv[8];
+        int pr[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const size_t o = ((size_t)b * S + s + q) * n + j;
+            pv[q] = pval[o];
+            pr[q] = prow[o];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (pv[q] < best) { best = pv[q]; brow = pr[q]; }
+    }
+    for (; s < S; ++s) {
         const size_t o = ((size_t)b * S + s) * n + j;
         CT v = pval[o];
         if (v < best) { best = v; brow = prow[o]; }
@@ -148,6 +162,7 @@ __global__ void k_min_trick_final(const double* __restrict__ pval, int S, int n,
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     double best = INFINITY;
+#pragma unroll 8
     for (int s = 0; s < S; ++s) {
         double t = pval[((size_t)b * S + s) * n + j];
         best = t < best ? t : best;

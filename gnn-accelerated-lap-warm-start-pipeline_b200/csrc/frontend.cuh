@@ -59,13 +59,18 @@ __device__ __forceinline__ void sort_small(int* a, int m) {
     }
 }
 
-template <typename CT, int VEC, int EPT>
+// One barrier per row: the tight list of row r is double-buffered and finalised (sorted, written
+// out) by thread 0 AFTER the min-reduction barrier of row r+1, when every thread has finished
+// row r's tight pass.  VSM keeps v in shared memory instead of registers (long rows: 16 binary64
+// registers per thread would spill under the 64-register cap of a 1024-thread CTA).
+template <typename CT, int VEC, int EPT, bool VSM>
 __global__ void __launch_bounds__(1024) k_front_end(
     const CT* __restrict__ C, long long inst_stride, int ld, int n, int rows_per_cta,
     const double* __restrict__ u_seed, const double* __restrict__ v_seed /* [B][n] */, double eps, double tight_eps,
     double* __restrict__ u_tight /* [B][n] */, int* __restrict__ tight_cols /* [B][n][kTightCap] */,
     int* __restrict__ tight_cnt /* [B][n] */, FrontFlags* __restrict__ flags /* [B] */)
 {
+    B200LAP_DYN_SMEM(dyn);
     __shared__ BlockRed s_red;
     __shared__ int s_cnt[2];
     __shared__ int s_list[2][kTightCap];
@@ -73,18 +78,35 @@ __global__ void __launch_bounds__(1024) k_front_end(
     const CT* base = C + (size_t)b * inst_stride;
     const double* vs = v_seed + (size_t)b * n;
     const double* us = u_seed + (size_t)b * n;
+    double* sv = reinterpret_cast<double*>(dyn);
     if (tid < 2) s_cnt[tid] = 0;
-    double vv[EPT];
+    double vv[VSM ? 1 : EPT];
+    if constexpr (VSM) {
+        for (int j = tid; j < n; j += T) sv[j] = vs[j];
+    } else {
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        const int col = owned_col<VEC>(e, T, tid);
-        vv[e] = col < n ? vs[col] : 0.0;
+        for (int e = 0; e < EPT; ++e) {
+            const int col = owned_col<VEC>(e, T, tid);
+            vv[e] = col < n ? vs[col] : 0.0;
+        }
     }
     __syncthreads();
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(n, r0 + rows_per_cta);
     int viol = 0, infeas = 0, par = 0, rpar = 0;
     unsigned long long total = 0;
+    double ut_prev = 0.0;
+    auto finalize = [&](int r, int p, double ut) {     // thread 0 only
+        const int c = s_cnt[p];
+        s_cnt[p] = 0;
+        const int m2 = c < kTightCap ? c : kTightCap;
+        sort_small(s_list[p], m2);
+        int* out = tight_cols + ((size_t)b * n + r) * kTightCap;
+        for (int q = 0; q < m2; ++q) out[q] = s_list[p][q];
+        tight_cnt[(size_t)b * n + r] = c;
+        u_tight[(size_t)b * n + r] = ut;
+        total += (unsigned long long)c;
+    };
     for (int r = r0; r < r1; ++r) {
         const CT* crow = base + (size_t)r * ld;
         CT cv[EPT];
@@ -100,41 +122,37 @@ __global__ void __launch_bounds__(1024) k_front_end(
         double m = INFINITY;
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
-            if (owned_col<VEC>(e, T, tid) < n) {
+            const int col = owned_col<VEC>(e, T, tid);
+            if (col < n) {
                 const double c = (double)cv[e];
-                viol |= ((ui + vv[e]) - c > eps);
-                infeas |= ((c - ui) - vv[e] < -eps);
-                const double red = c - vv[e];
+                const double vj = VSM ? sv[col] : vv[VSM ? 0 : e];
+                viol |= ((ui + vj) - c > eps);
+                infeas |= ((c - ui) - vj < -eps);
+                const double red = c - vj;
                 m = red < m ? red : m;
             }
         }
         rpar ^= 1;
         const double ut = block_min_d(s_red, rpar, m);
+        // every thread has finished the tight pass of row r-1: its list is complete
+        if (tid == 0 && r > r0) finalize(r - 1, par ^ 1, ut_prev);
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const int col = owned_col<VEC>(e, T, tid);
             if (col < n) {
-                const double rr = ((double)cv[e] - ut) - vv[e];
+                const double vj = VSM ? sv[col] : vv[VSM ? 0 : e];
+                const double rr = ((double)cv[e] - ut) - vj;
                 if (fabs(rr) <= tight_eps) {
                     const int slot = atomicAdd(&s_cnt[par], 1);
                     if (slot < kTightCap) s_list[par][slot] = col;
                 }
             }
         }
-        __syncthreads();
-        if (tid == 0) {
-            const int c = s_cnt[par];
-            s_cnt[par] = 0;
-            const int m2 = c < kTightCap ? c : kTightCap;
-            sort_small(s_list[par], m2);
-            int* out = tight_cols + ((size_t)b * n + r) * kTightCap;
-            for (int q = 0; q < m2; ++q) out[q] = s_list[par][q];
-            tight_cnt[(size_t)b * n + r] = c;
-            u_tight[(size_t)b * n + r] = ut;
-            total += (unsigned long long)c;
-        }
+        ut_prev = ut;
         par ^= 1;
     }
+    __syncthreads();
+    if (tid == 0 && r1 > r0) finalize(r1 - 1, par ^ 1, ut_prev);
     if (viol) atomicOr(&flags[b].any_viol, 1);
     if (infeas) atomicOr(&flags[b].infeasible, 1);
     if (tid == 0 && total) atomicAdd(&flags[b].total_tight, total);
