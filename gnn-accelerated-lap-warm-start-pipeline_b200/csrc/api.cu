@@ -14,6 +14,7 @@
 #include "solver.cuh"
 #include "features.cuh"
 #include "mlp.cuh"
+#include "mlp_tc.cuh"
 #include "../../include/b200lap.h"
 
 using namespace b200lap;
@@ -56,6 +57,7 @@ struct b200lap_ctx {
     int force_global_state = 0;  // option: keep solver state in global memory (tests)
     int front_rows_per_cta = 0;  // option
     int mlp_impl = 0;            // option: 0 = default
+    int feat_ept = 0;            // option: entries per thread of the row-feature kernel (0 = auto)
     std::mutex mu;
 
     void ws_reset() {
@@ -163,17 +165,35 @@ __global__ void k_force_slow_path(FrontFlags* flags, int batch) {
     if (b < batch) flags[b].any_viol = 1;
 }
 
-template <typename CT, int VEC, int EPT>
-int launch_front(b200lap_ctx* ctx, int T, int rows_per_cta, const CT* C, long long inst_stride, int ld, int batch, int n,
-                  const double* u, const double* v, double eps, double tol, double* u_tight, int* tl, int* tc, FrontFlags* flags)
+template <typename CT, int VEC, int EPT, bool VSM, int MAXT>
+int launch_front(b200lap_ctx* ctx, int rows_per_cta, const CT* C, long long inst_stride, int ld, int batch, int n,
+                 const double* u, const double* v, double eps, double tol, double* u_tight, int* tl, int* tc, FrontFlags* flags)
 {
+    const int T = round_up((n + EPT - 1) / EPT, 32);
     dim3 grid((n + rows_per_cta - 1) / rows_per_cta, batch);
-    constexpr bool kVsm = EPT >= 16;
-    auto k = k_front_end<CT, VEC, EPT, kVsm>;
-    const size_t smem = kVsm ? (size_t)n * sizeof(double) : 0;
+    auto k = k_front_end<CT, VEC, EPT, VSM, MAXT>;
+    const size_t smem = VSM ? (size_t)n * sizeof(double) : 0;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200LAP_LAUNCH(k, grid, dim3(T), smem, ctx->stream, C, inst_stride, ld, n, rows_per_cta, u, v, eps, tol, u_tight, tl, tc, flags);
     ctx->launches += 1;
+    return 0;
+}
+
+// Few warps per row with many entries per thread: the per-row block reduction and loop overhead are
+// per-thread costs (ncu: the 4-entries-per-thread version issued 62 instructions per matrix entry).
+template <typename CT, int VEC>
+int dispatch_front(b200lap_ctx* ctx, int R, const CT* C, long long inst_stride, int ld, int batch, int n, const double* u,
+                   const double* v, double eps, double tol, double* u_tight, int* tl, int* tc, FrontFlags* flags, bool* done)
+{
+#define FRONT(EPT_, VSM_, MAXT_) \
+    return launch_front<CT, VEC, EPT_, VSM_, MAXT_>(ctx, R, C, inst_stride, ld, batch, n, u, v, eps, tol, u_tight, tl, tc, flags)
+    *done = true;
+    if (n <= 1024) FRONT(4, false, 256);
+    if (n <= 4096) FRONT(16, false, 256);
+    if (n <= 8192) FRONT(32, true, 256);
+    if (n <= 16384) FRONT(32, true, 512);
+#undef FRONT
+    *done = false;
     return 0;
 }
 
@@ -186,21 +206,9 @@ int run_front_end(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, 
     int R = ctx->front_rows_per_cta > 0 ? ctx->front_rows_per_cta : (n >= 8192 ? 16 : (n >= 1024 ? 8 : 2));
     const bool vec = vec_ok(C, inst_stride, ld, n);
     constexpr int V = natural_vec<CT>();
-    bool done = true;
-    int fr = 0;
-#define FRONT(VEC_, EPT_)                                                                                             \
-    fr = launch_front<CT, VEC_, EPT_>(ctx, round_up((n + (EPT_) - 1) / (EPT_), 32), R, C, inst_stride, ld, batch, n, u, v, \
-                                      eps, tol, u_tight, tl, tc, flags)
-    if (vec && n <= 1024 * V) FRONT(V, V);
-    else if (vec && n <= 1024 * 2 * V) FRONT(V, 2 * V);
-    else if (vec && n <= 1024 * 4 * V) FRONT(V, 4 * V);
-    else if (n <= 1024) FRONT(1, 1);
-    else if (n <= 2048) FRONT(1, 2);
-    else if (n <= 4096) FRONT(1, 4);
-    else if (n <= 8192) FRONT(1, 8);
-    else if (n <= 16384) FRONT(1, 16);
-    else done = false;
-#undef FRONT
+    bool done = false;
+    int fr = vec ? dispatch_front<CT, V>(ctx, R, C, inst_stride, ld, batch, n, u, v, eps, tol, u_tight, tl, tc, flags, &done)
+                 : dispatch_front<CT, 1>(ctx, R, C, inst_stride, ld, batch, n, u, v, eps, tol, u_tight, tl, tc, flags, &done);
     if (fr) return fr;
     if (!done) {
         // row too long for the register-resident sweep: the solver kernel runs the (sequential)
@@ -361,6 +369,7 @@ int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value) {
     else if (k == "force_global_state") ctx->force_global_state = (int)value;
     else if (k == "front_rows_per_cta") ctx->front_rows_per_cta = (int)value;
     else if (k == "mlp_impl") ctx->mlp_impl = (int)value;
+    else if (k == "feat_ept") ctx->feat_ept = (int)value;
     else return fail(B200LAP_ERR_ARG, "unknown option " + k);
     return 0;
 }

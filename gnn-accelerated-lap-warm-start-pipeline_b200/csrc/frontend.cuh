@@ -63,8 +63,8 @@ __device__ __forceinline__ void sort_small(int* a, int m) {
 // out) by thread 0 AFTER the min-reduction barrier of row r+1, when every thread has finished
 // row r's tight pass.  VSM keeps v in shared memory instead of registers (long rows: 16 binary64
 // registers per thread would spill under the 64-register cap of a 1024-thread CTA).
-template <typename CT, int VEC, int EPT, bool VSM>
-__global__ void __launch_bounds__(1024) k_front_end(
+template <typename CT, int VEC, int EPT, bool VSM, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_front_end(
     const CT* __restrict__ C, long long inst_stride, int ld, int n, int rows_per_cta,
     const double* __restrict__ u_seed, const double* __restrict__ v_seed /* [B][n] */, double eps, double tight_eps,
     double* __restrict__ u_tight /* [B][n] */, int* __restrict__ tight_cols /* [B][n][kTightCap] */,
@@ -82,7 +82,17 @@ __global__ void __launch_bounds__(1024) k_front_end(
     if (tid < 2) s_cnt[tid] = 0;
     double vv[VSM ? 1 : EPT];
     if constexpr (VSM) {
-        for (int j = tid; j < n; j += T) sv[j] = vs[j];
+        if constexpr (VEC == 4) {
+            // split layout: a thread's 4 columns are two 16-byte loads, each conflict-free across the warp
+            double2* sa = reinterpret_cast<double2*>(sv);
+            double2* sb = sa + n / 4;
+            for (int gi = tid; gi < n / 4; gi += T) {
+                sa[gi] = make_double2(vs[4 * gi], vs[4 * gi + 1]);
+                sb[gi] = make_double2(vs[4 * gi + 2], vs[4 * gi + 3]);
+            }
+        } else {
+            for (int j = tid; j < n; j += T) sv[j] = vs[j];
+        }
     } else {
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
@@ -107,6 +117,17 @@ __global__ void __launch_bounds__(1024) k_front_end(
         u_tight[(size_t)b * n + r] = ut;
         total += (unsigned long long)c;
     };
+    auto v_of = [&](int e, int col) -> double {
+        if constexpr (!VSM) {
+            return vv[e];
+        } else if constexpr (VEC == 4) {
+            const double2* sa = reinterpret_cast<const double2*>(sv);
+            const double2 t = (e & 2) ? sa[n / 4 + (col >> 2)] : sa[col >> 2];   // the compiler merges the 4 uses of a group
+            return (e & 1) ? t.y : t.x;
+        } else {
+            return sv[col];
+        }
+    };
     for (int r = r0; r < r1; ++r) {
         const CT* crow = base + (size_t)r * ld;
         CT cv[EPT];
@@ -125,7 +146,7 @@ __global__ void __launch_bounds__(1024) k_front_end(
             const int col = owned_col<VEC>(e, T, tid);
             if (col < n) {
                 const double c = (double)cv[e];
-                const double vj = VSM ? sv[col] : vv[VSM ? 0 : e];
+                const double vj = v_of(e, col);
                 viol |= ((ui + vj) - c > eps);
                 infeas |= ((c - ui) - vj < -eps);
                 const double red = c - vj;
@@ -140,7 +161,7 @@ __global__ void __launch_bounds__(1024) k_front_end(
         for (int e = 0; e < EPT; ++e) {
             const int col = owned_col<VEC>(e, T, tid);
             if (col < n) {
-                const double vj = VSM ? sv[col] : vv[VSM ? 0 : e];
+                const double vj = v_of(e, col);
                 const double rr = ((double)cv[e] - ut) - vj;
                 if (fabs(rr) <= tight_eps) {
                     const int slot = atomicAdd(&s_cnt[par], 1);
