@@ -39,7 +39,6 @@ struct SolverShared {
     int s_list[kTightCap];
     int hi, final_j, next_row, aux;
     int minw[3], maxw[3];   // hit-word ranges, rotated over 3 steps (reset one step after use)
-    int hit_cnt[3], hit_j[3], hit_k[3];   // number of hits of a relax step and the first one recorded
     unsigned int cursor, deferred;
     long long tr[kTraceWords];
 };
@@ -70,7 +69,7 @@ template <typename CT> struct SolveArgs {
 
 __host__ __device__ inline size_t solver_state_bytes(int n) {
     const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
-    return n8 * 8 * 2 + n8 * 4 * 6 + 3 * (((size_t)n + 31) / 32 + 4) * 4;   // three rotating hit bitmaps
+    return n8 * 8 * 2 + n8 * 4 * 6 + (((size_t)n + 31) / 32 + 4) * 4;
 }
 
 template <typename CT> struct SolverCtx {
@@ -78,8 +77,7 @@ template <typename CT> struct SolverCtx {
     int ld, n;
     double *v, *d;
     int *pred, *cols, *pos, *y, *x, *free_rows;
-    unsigned int* bitmap;   // 3 bitmaps of `bw` words, selected by step % 3 like the hit-word ranges
-    int bw;
+    unsigned int* bitmap;
     SolverShared* sh;
     Red R;
     int step;   // relax/collect step counter (selects the minw/maxw slot)
@@ -115,7 +113,7 @@ __device__ __forceinline__ void row_scan(const CT* __restrict__ crow, int n, F&&
 // mode 1: relax (_scan_dense): every flagged position reached the level; the first unmatched
 //         one ends the path search.
 template <typename CT>
-__device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, unsigned int* bm, int lo, int wlo, int whi)
+__device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo, int whi)
 {
     // executed by warp 0 only
     const int lane = lane_id();
@@ -123,7 +121,7 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, unsigned int* b
     double level = INFINITY;
     for (int w0 = wlo; w0 <= whi; w0 += 32) {
         unsigned int bits = 0;
-        if (w0 + lane <= whi) { bits = bm[w0 + lane]; bm[w0 + lane] = 0u; }
+        if (w0 + lane <= whi) { bits = S.bitmap[w0 + lane]; S.bitmap[w0 + lane] = 0u; }
         unsigned int nz = __ballot_sync(kFull, bits != 0u);
         while (nz) {
             const int l = __ffs((int)nz) - 1;
@@ -160,13 +158,13 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, unsigned int* b
 }
 
 template <typename CT>
-__device__ __forceinline__ void replay_relax(SolverCtx<CT>& S, unsigned int* bm, int hi_in, int wlo, int whi)
+__device__ __forceinline__ void replay_relax(SolverCtx<CT>& S, int hi_in, int wlo, int whi)
 {
     const int lane = lane_id();
     int hi = hi_in, fin = -1;
     for (int w0 = wlo; w0 <= whi; w0 += 32) {
         unsigned int bits = 0;
-        if (w0 + lane <= whi) { bits = bm[w0 + lane]; bm[w0 + lane] = 0u; }
+        if (w0 + lane <= whi) { bits = S.bitmap[w0 + lane]; S.bitmap[w0 + lane] = 0u; }
         unsigned int nz = __ballot_sync(kFull, bits != 0u);
         while (nz) {
             const int l = __ffs((int)nz) - 1;
@@ -205,26 +203,9 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
     });
     __syncthreads();
     int lo = 0, hi = 0, n_ready = 0, final_j = -1;
-    // A relax step with exactly ONE hit (the common case) is finished without a second barrier and
-    // without the serial replay: every thread learns (j, k) of the hit, owners update pos[] of the two
-    // swapped columns themselves, and the two cols[] writes are deferred -- kept in (uniform) registers
-    // as a pending swap, written to shared memory by thread 0 one step later and consulted from the
-    // registers until a barrier has made that write visible.
-    struct Pend { int valid, k, h, j, c; };   // cols[k] = c ; cols[h] = j
-    Pend pn{0, 0, 0, 0, 0}, po{0, 0, 0, 0, 0};
-    auto cols_at = [&](int p) -> int {
-        if (pn.valid) { if (p == pn.h) return pn.j; if (p == pn.k) return pn.c; }
-        if (po.valid) { if (p == po.h) return po.j; if (p == po.k) return po.c; }
-        return S.cols[p];
-    };
     while (final_j < 0) {
         if (lo == hi) {
             // ---- level collect: positions [lo, n) in blocked ownership, prefix-min records flagged
-            if (pn.valid || po.valid) {
-                if (tid == 0 && pn.valid) { S.cols[pn.k] = pn.c; S.cols[pn.h] = pn.j; }
-                __syncthreads();     // pending cols[] writes are now visible to the blocked readers below
-                pn.valid = 0; po.valid = 0;
-            }
             n_ready = lo;
             const int L = n - lo;
             const int chunk = (L + T - 1) / T;
@@ -249,13 +230,12 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                 before = wmin < before ? wmin : before;
             }
             const int sp = S.step % 3;
-            unsigned int* bm = S.bitmap + sp * S.bw;
             int wmin_i = 0x7fffffff, wmax_i = -1;
             double run = before;
             for (int k = k0; k < k1; ++k) {
                 const double dj = S.d[S.cols[k]];
                 if (dj <= run) {
-                    atomicOr(&bm[k >> 5], 1u << (k & 31));
+                    atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
                     wmin_i = min(wmin_i, k >> 5);
                     wmax_i = max(wmax_i, k >> 5);
                     run = dj;
@@ -267,11 +247,11 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                 int wlo = sh->minw[sp], whi = sh->maxw[sp];
                 if (lane_id() == 0) {
                     const int old_slot = (sp + 2) % 3;
-                    sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1; sh->hit_cnt[old_slot] = 0;
+                    sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1;
                     sh->tr[TR_COLLECT]++;
                 }
                 if (whi < 0) { wlo = lo >> 5; whi = wlo; }
-                replay_collect(S, bm, lo, wlo, whi);
+                replay_collect(S, lo, wlo, whi);
             }
             __syncthreads();
             S.step++;
@@ -280,7 +260,7 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
         }
         // ---- relax from every SCAN column in turn (_scan_dense)
         while (final_j < 0 && lo != hi) {
-            const int js = cols_at(lo);
+            const int js = S.cols[lo];
             const int i = S.y[js];
             const double level = S.d[js];
             ++lo;
@@ -288,7 +268,6 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
             const CT c_js = __ldg(crow + js);        // issued together with the row loads below
             const double v_js = S.v[js];
             const int sp = S.step % 3;
-            unsigned int* bm = S.bitmap + sp * S.bw;
             int wmin_i = 0x7fffffff, wmax_i = -1;
             row_scan<MAXC>(crow, n, [&](int j, double c) {
                 const double slack = ((double)c_js - v_js) - level;
@@ -299,10 +278,9 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                         S.d[j] = cand;
                         S.pred[j] = i;
                         if (cand == level) {
-                            atomicOr(&bm[k >> 5], 1u << (k & 31));
+                            atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
                             wmin_i = min(wmin_i, k >> 5);
                             wmax_i = max(wmax_i, k >> 5);
-                            if (atomicAdd(&sh->hit_cnt[sp], 1) == 0) { sh->hit_j[sp] = j; sh->hit_k[sp] = k; }
                         }
                     }
                 }
@@ -310,46 +288,27 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
             if (wmax_i >= 0) { atomicMin(&sh->minw[sp], wmin_i); atomicMax(&sh->maxw[sp], wmax_i); }
             __syncthreads();
             S.step++;
-            const int nhit = sh->hit_cnt[sp];
+            const int whi = sh->maxw[sp];
             if (tid == 0) {
                 // the slot used one step ago has been read by everyone (they all passed this barrier);
                 // it is next written two steps from now, after another barrier
                 const int old_slot = (sp + 2) % 3;
-                sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1; sh->hit_cnt[old_slot] = 0;
+                sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1;
                 sh->tr[TR_RELAX]++;
-                // last step's pending swap goes to shared memory now; it stays in `po` for this step
-                if (pn.valid) { S.cols[pn.k] = pn.c; S.cols[pn.h] = pn.j; }
             }
-            po = pn;
-            pn.valid = 0;
-            if (nhit == 1) {
-                const int j1 = sh->hit_j[sp], k1 = sh->hit_k[sp];
-                if (tid == j1 % T) bm[k1 >> 5] = 0u;             // the only bit of this step's bitmap (reused 3 steps on)
-                if (S.y[j1] < 0) {
-                    final_j = j1;                                  // unmatched column reached: the path ends here
-                } else {
-                    const int c2 = cols_at(hi);                    // (po is consulted: its write may not be visible yet)
-                    pn.valid = 1; pn.k = k1; pn.h = hi; pn.j = j1; pn.c = c2;
-                    if (tid == j1 % T) S.pos[j1] = hi;
-                    if (tid == c2 % T) S.pos[c2] = k1;
-                    ++hi;
-                }
-            } else if (nhit > 1) {
+            if (whi >= 0) {
                 if (warp_id() == 0) {
-                    const int wlo = sh->minw[sp], whi = sh->maxw[sp];
-                    // thread 0 wrote every pending swap above (program order), make it visible to the warp
-                    __syncwarp();
-                    replay_relax(S, bm, hi, wlo, whi);
+                    const int wlo = sh->minw[sp];
+                    replay_relax(S, hi, wlo, whi);
                 }
                 __syncthreads();
-                po.valid = 0;
                 hi = sh->hi;
                 final_j = sh->final_j;
             }
         }
     }
     // ---- dual update of the READY columns (lapjv.cpp:270-276); lo of the caller == n_ready
-    const double level = S.d[cols_at(n_ready)];
+    const double level = S.d[S.cols[n_ready]];
     for (int j = tid; j < n; j += T)
         if (S.pos[j] < n_ready) S.v[j] += S.d[j] - level;
     return final_j;
@@ -562,11 +521,9 @@ __global__ void __launch_bounds__(1024, 1) k_solve(SolveArgs<CT> a)
         sh.s_cnt = 0;
         sh.minw[0] = sh.minw[1] = sh.minw[2] = 0x7fffffff;
         sh.maxw[0] = sh.maxw[1] = sh.maxw[2] = -1;
-        sh.hit_cnt[0] = sh.hit_cnt[1] = sh.hit_cnt[2] = 0;
         for (int q = 0; q < kTraceWords; ++q) sh.tr[q] = 0;
     }
-    S.bw = (n + 31) / 32 + 4;
-    for (int w = tid; w < 3 * S.bw; w += T) S.bitmap[w] = 0u;
+    for (int w = tid; w < (n + 31) / 32 + 4; w += T) S.bitmap[w] = 0u;
     const CT* colmin = a.colmin + (size_t)b * n;
     const int* colarg = a.colarg + (size_t)b * n;
     int rc = 0;
