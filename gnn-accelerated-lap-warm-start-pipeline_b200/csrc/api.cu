@@ -262,7 +262,7 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
     const int per_thread = (n + T - 1) / T;      // row entries a thread keeps in registers per step
 #define SOLVE(MAXC_)                                                                                                       \
     do {                                                                                                                   \
-        auto k = k_solve<CT, MAXC_>;                                                                                       \
+        auto k = T <= 512 ? k_solve<CT, MAXC_, 512> : k_solve<CT, MAXC_, 1024>;                                            \
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024))); \
         B200LAP_LAUNCH(k, dim3(batch), dim3(T), smem, ctx->stream, a);                                                     \
     } while (0)

@@ -40,6 +40,7 @@ struct SolverShared {
     int hi, final_j, next_row, aux;
     int minw[3], maxw[3];   // hit-word ranges, rotated over 3 steps (reset one step after use)
     unsigned int cursor, deferred;
+    int hitk[32];           // positions of the flagged records of a collect step, ascending
     long long tr[kTraceWords];
 };
 
@@ -119,7 +120,53 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
     const int lane = lane_id();
     int hi = lo;
     double level = INFINITY;
-    for (int w0 = wlo; w0 <= whi; w0 += 32) {
+    bool done = false;
+    if (whi - wlo < 32) {
+        // Common case (a handful of prefix-minimum records): enumerate the set bits into lanes, fetch
+        // (position, column, distance) of every record IN PARALLEL -- they are not touched by the swaps
+        // of earlier records -- and leave only the cols[hi] read on lane 0's serial chain.
+        unsigned int bits = 0;
+        if (wlo + lane <= whi) { bits = S.bitmap[wlo + lane]; S.bitmap[wlo + lane] = 0u; }
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(kFull, incl, 31);
+        if (total <= 32) {
+            int slot = incl - cnt;
+            unsigned int w = bits;
+            while (w) {
+                const int bpos = __ffs((int)w) - 1;
+                w &= w - 1;
+                S.sh->hitk[slot++] = (wlo + lane) * 32 + bpos;
+            }
+            __syncwarp();
+            int my_k = 0, my_j = 0;
+            double my_d = INFINITY;
+            if (lane < total) { my_k = S.sh->hitk[lane]; my_j = S.cols[my_k]; my_d = S.d[my_j]; }
+            for (int h = 0; h < total; ++h) {
+                const int k = __shfl_sync(kFull, my_k, h);
+                const int j = __shfl_sync(kFull, my_j, h);
+                const double dj = __shfl_sync(kFull, my_d, h);
+                if (lane == 0) {
+                    if (dj < level) { hi = lo; level = dj; }
+                    const int c2 = S.cols[hi];
+                    S.cols[k] = c2; S.pos[c2] = k;
+                    S.cols[hi] = j; S.pos[j] = hi;
+                    ++hi;
+                }
+            }
+            done = true;
+        } else {
+            // put the words back for the general path below
+            if (wlo + lane <= whi) S.bitmap[wlo + lane] = bits;
+            __syncwarp();
+        }
+    }
+    for (int w0 = wlo; !done && w0 <= whi; w0 += 32) {
         unsigned int bits = 0;
         if (w0 + lane <= whi) { bits = S.bitmap[w0 + lane]; S.bitmap[w0 + lane] = 0u; }
         unsigned int nz = __ballot_sync(kFull, bits != 0u);
@@ -212,7 +259,20 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
             const int k0 = lo + tid * chunk;
             const int k1 = min(n, k0 + chunk);
             double lm = INFINITY;
-            for (int k = k0; k < k1; ++k) { const double t = S.d[S.cols[k]]; lm = t < lm ? t : lm; }
+            // the thread's chunk of distances is gathered ONCE, as independent loads, and kept in registers
+            constexpr int kChunkRegs = MAXC > 0 ? MAXC : 1;
+            double dch[kChunkRegs];
+            if constexpr (MAXC > 0) {
+                int cj[MAXC];
+#pragma unroll
+                for (int q = 0; q < MAXC; ++q) cj[q] = (q < chunk && k0 + q < k1) ? S.cols[k0 + q] : -1;
+#pragma unroll
+                for (int q = 0; q < MAXC; ++q) dch[q] = cj[q] >= 0 ? S.d[cj[q]] : INFINITY;
+#pragma unroll
+                for (int q = 0; q < MAXC; ++q) lm = dch[q] < lm ? dch[q] : lm;
+            } else {
+                for (int k = k0; k < k1; ++k) { const double t = S.d[S.cols[k]]; lm = t < lm ? t : lm; }
+            }
             double incl = lm;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -232,14 +292,20 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
             const int sp = S.step % 3;
             int wmin_i = 0x7fffffff, wmax_i = -1;
             double run = before;
-            for (int k = k0; k < k1; ++k) {
-                const double dj = S.d[S.cols[k]];
+            auto flag_record = [&](int k, double dj) {
                 if (dj <= run) {
                     atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
                     wmin_i = min(wmin_i, k >> 5);
                     wmax_i = max(wmax_i, k >> 5);
                     run = dj;
                 }
+            };
+            if constexpr (MAXC > 0) {
+#pragma unroll
+                for (int q = 0; q < MAXC; ++q)
+                    if (q < chunk && k0 + q < k1) flag_record(k0 + q, dch[q]);
+            } else {
+                for (int k = k0; k < k1; ++k) flag_record(k, S.d[S.cols[k]]);
             }
             if (wmax_i >= 0) { atomicMin(&sh->minw[sp], wmin_i); atomicMax(&sh->maxw[sp], wmax_i); }
             __syncthreads();
@@ -269,12 +335,10 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
             const double v_js = S.v[js];
             const int sp = S.step % 3;
             int wmin_i = 0x7fffffff, wmax_i = -1;
-            row_scan<MAXC>(crow, n, [&](int j, double c) {
-                const double slack = ((double)c_js - v_js) - level;
-                const int k = S.pos[j];
+            auto relax_one = [&](int j, int k, double c, double vj, double dj, double slack) {
                 if (k >= hi) {
-                    const double cand = (c - S.v[j]) - slack;
-                    if (cand < S.d[j]) {
+                    const double cand = (c - vj) - slack;
+                    if (cand < dj) {
                         S.d[j] = cand;
                         S.pred[j] = i;
                         if (cand == level) {
@@ -284,7 +348,33 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                         }
                     }
                 }
-            });
+            };
+            if constexpr (MAXC > 0) {
+                // every load of the step (matrix row AND the thread's pos/v/d entries) is issued before the
+                // first dependent instruction: the compiler cannot hoist shared loads over the stores of the
+                // previous column by itself, and a column-at-a-time body costs ~700 cycles per column
+                CT cr[MAXC];
+                int kq[MAXC];
+                double vq[MAXC], dq[MAXC];
+#pragma unroll
+                for (int q = 0; q < MAXC; ++q) {
+                    const int j = tid + q * T;
+                    cr[q] = j < n ? __ldg(crow + j) : (CT)0;
+                }
+#pragma unroll
+                for (int q = 0; q < MAXC; ++q) {
+                    const int j = tid + q * T;
+                    kq[q] = j < n ? S.pos[j] : -1;
+                    vq[q] = j < n ? S.v[j] : 0.0;
+                    dq[q] = j < n ? S.d[j] : 0.0;
+                }
+                const double slack = ((double)c_js - v_js) - level;
+#pragma unroll
+                for (int q = 0; q < MAXC; ++q) relax_one(tid + q * T, kq[q], (double)cr[q], vq[q], dq[q], slack);
+            } else {
+                const double slack = ((double)c_js - v_js) - level;
+                for (int j = tid; j < n; j += T) relax_one(j, S.pos[j], (double)crow[j], S.v[j], S.d[j], slack);
+            }
             if (wmax_i >= 0) { atomicMin(&sh->minw[sp], wmin_i); atomicMax(&sh->maxw[sp], wmax_i); }
             __syncthreads();
             S.step++;
@@ -489,8 +579,8 @@ __device__ void cold_solve(SolverCtx<CT>& S, const CT* colmin, const int* colarg
 }
 
 // ---- the persistent per-instance kernel -----------------------------------------------------------
-template <typename CT, int MAXC>
-__global__ void __launch_bounds__(1024, 1) k_solve(SolveArgs<CT> a)
+template <typename CT, int MAXC, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
 {
     B200LAP_DYN_SMEM(dyn);
     __shared__ SolverShared sh;

@@ -313,3 +313,28 @@ def test_min_trick_exact_at_full_size(ctx):
     m = C.min(dim=0)
     assert torch.equal(colmin[0], m.values)
     assert torch.equal(C[colarg[0].long(), torch.arange(n, device="cuda")], m.values)
+
+
+def test_tensor_core_mlp_matches_ffma_path(ctx):
+    """hidden=192 runs on tcgen05 (3xTF32, csrc/mlp_tc.cuh) by default; the FFMA tile kernel (csrc/mlp.cuh, ctx
+    option mlp_impl=1) is the same math in plain binary32.  Both must agree to binary32 rounding level, with and
+    without the cost branch, including a ragged last tile (n % 128 != 0) and a batch."""
+    import torch
+    import b200lap
+    from gnn.one_gnn import OneGNN
+    torch.manual_seed(0)
+    module = OneGNN(21, hidden=192, layers=4, dropout=0.1, topk=16).eval()
+    model = b200lap.Model(ctx, module.state_dict(), topk=16)
+    for n, B in ((77, 1), (300, 3), (2048, 2)):
+        Cs = np.stack([c for _, c in gen.mixed_batch(n, B, first_seed=9)]).astype(np.float32)
+        Cd = torch.from_numpy(Cs).cuda()
+        feat, topv = ctx.row_features(Cd, topk=16)
+        for tv in (topv, None):
+            ctx.set_option("mlp_impl", 1)
+            u1, r1 = ctx.onegnn_forward(model, feat, tv, want_raw=True)
+            ctx.set_option("mlp_impl", 0)
+            u0, r0 = ctx.onegnn_forward(model, feat, tv, want_raw=True)
+            ctx.sync()
+            scale = float(r1.abs().max())
+            assert float((r0 - r1).abs().max()) <= 2e-5 * scale, (n, B, tv is None)
+            assert float((u0 - u1).abs().max()) <= 2e-5 * scale
