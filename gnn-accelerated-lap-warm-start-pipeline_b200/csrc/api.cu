@@ -246,10 +246,11 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
     }
     a.colmin = colmin; a.colarg = colarg;
     const size_t state = solver_state_bytes(n);
-    a.use_smem = (!ctx->force_global_state && state <= (size_t)ctx->max_dyn_smem) ? 1 : 0;
+    size_t smem = 0;
+    a.smem_mask = solver_place_state(n, ctx->force_global_state ? 0 : (size_t)ctx->max_dyn_smem, &smem);
     a.gws = nullptr; a.gws_stride = 0;
-    if (!a.use_smem) {
-        const size_t stride = (state + 255) & ~(size_t)255;
+    if (a.smem_mask != (1 << ST_COUNT) - 1) {
+        const size_t stride = (state + 4096 + 255) & ~(size_t)255;
         unsigned char* g = (unsigned char*)ctx->take(stride * (size_t)batch);
         if (!g) return fail(-1, "device workspace allocation failed (solver state)");
         a.gws = g; a.gws_stride = (long long)stride;
@@ -258,7 +259,6 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
     int T = ctx->solver_threads > 0 ? ctx->solver_threads : round_up((n + 3) / 4, 32);
     if (T > 1024) T = 1024;
     if (T < 32) T = 32;
-    const size_t smem = a.use_smem ? state : 0;
     const int per_thread = (n + T - 1) / T;      // row entries a thread keeps in registers per step
 #define SOLVE(MAXC_)                                                                                                       \
     do {                                                                                                                   \
@@ -367,6 +367,7 @@ int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value) {
     const std::string k(key);
     if (k == "solver_threads") ctx->solver_threads = (int)value;
     else if (k == "force_global_state") ctx->force_global_state = (int)value;
+    else if (k == "solver_smem_budget") ctx->max_dyn_smem = value > 0 ? (int)value : 227 * 1024 - 4096;
     else if (k == "front_rows_per_cta") ctx->front_rows_per_cta = (int)value;
     else if (k == "mlp_impl") ctx->mlp_impl = (int)value;
     else if (k == "feat_ept") ctx->feat_ept = (int)value;

@@ -60,13 +60,37 @@ template <typename CT> struct SolveArgs {
     const int* colarg;      // [B][n]
     unsigned char* gws;     // global state workspace, `gws_stride` bytes per instance (or null)
     long long gws_stride;
-    int use_smem;
+    int smem_mask;          // bit a set: state array a lives in shared memory (order of kStateArrays), else in gws
     int* x;                 // [B][n] out
     int* y;                 // [B][n] out
     int* rc;                // [B] out
     long long* trace;       // [B][kTraceWords] out (nullable)
     double* v_out;          // [B][n] final column potentials (nullable)
 };
+
+// State arrays in placement priority order (hottest first): a relax step reads d, pos, v of every
+// column; the replay and the path flip touch y, cols, pred, x sparsely.  Whatever fits goes to shared
+// memory, the rest to the (L2-resident) global workspace -- n = 8192 keeps d, pos, v, y on chip,
+// n = 16384 keeps d and pos.
+enum StateArray { ST_D = 0, ST_POS, ST_V, ST_Y, ST_COLS, ST_PRED, ST_X, ST_FREE, ST_BITMAP, ST_COUNT };
+__host__ __device__ inline size_t state_array_bytes(int a, int n) {
+    const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
+    if (a == ST_D || a == ST_V) return n8 * 8;
+    if (a == ST_BITMAP) return ((((size_t)n + 31) / 32 + 4) * 4 + 15) & ~(size_t)15;
+    return n8 * 4;
+}
+// greedy placement under a shared-memory budget -> (mask, shared bytes)
+__host__ inline int solver_place_state(int n, size_t budget, size_t* smem_bytes) {
+    int mask = 0;
+    size_t used = 0;
+    const int order[ST_COUNT] = {ST_BITMAP, ST_D, ST_POS, ST_V, ST_Y, ST_COLS, ST_PRED, ST_X, ST_FREE};
+    for (int q = 0; q < ST_COUNT; ++q) {
+        const size_t b = state_array_bytes(order[q], n);
+        if (used + b <= budget) { used += b; mask |= 1 << order[q]; }
+    }
+    *smem_bytes = used;
+    return mask;
+}
 
 __host__ __device__ inline size_t solver_state_bytes(int n) {
     const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
@@ -590,17 +614,25 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     S.ld = a.ld;
     S.n = n;
     {
-        unsigned char* base = a.use_smem ? dyn : a.gws + (size_t)b * a.gws_stride;
-        const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
-        S.v = (double*)base; base += n8 * 8;
-        S.d = (double*)base; base += n8 * 8;
-        S.pred = (int*)base; base += n8 * 4;
-        S.cols = (int*)base; base += n8 * 4;
-        S.pos = (int*)base; base += n8 * 4;
-        S.y = (int*)base; base += n8 * 4;
-        S.x = (int*)base; base += n8 * 4;
-        S.free_rows = (int*)base; base += n8 * 4;
-        S.bitmap = (unsigned int*)base;
+        unsigned char* sbase = dyn;
+        unsigned char* gbase = a.gws ? a.gws + (size_t)b * a.gws_stride : nullptr;
+        auto place = [&](int arr) -> void* {
+            const size_t bytes = state_array_bytes(arr, n);
+            unsigned char* p;
+            if (a.smem_mask & (1 << arr)) { p = sbase; sbase += bytes; }
+            else { p = gbase; gbase += bytes; }
+            return p;
+        };
+        // same order as solver_place_state so shared offsets match the host's byte count
+        S.bitmap = (unsigned int*)place(ST_BITMAP);
+        S.d = (double*)place(ST_D);
+        S.pos = (int*)place(ST_POS);
+        S.v = (double*)place(ST_V);
+        S.y = (int*)place(ST_Y);
+        S.cols = (int*)place(ST_COLS);
+        S.pred = (int*)place(ST_PRED);
+        S.x = (int*)place(ST_X);
+        S.free_rows = (int*)place(ST_FREE);
     }
     S.sh = &sh;
     S.R.r = &sh.red;

@@ -104,6 +104,24 @@ def test_solver_ties_and_known_answers(emu):
     _opt(lib, ctx, "solver_threads", 0)
 
 
+def test_solver_mixed_state_placement(emu):
+    """Large instances keep only the hottest state arrays (d, pos, v, ...) in shared memory and the rest in the
+    global workspace; a tiny shared budget forces the same split on a small instance."""
+    lib, ctx = emu
+    _opt(lib, ctx, "solver_threads", 32)
+    rng = np.random.default_rng(4)
+    for budget in (1500, 2600, 4000):
+        _opt(lib, ctx, "solver_smem_budget", budget)
+        for fam in ("uniform", "clustered"):
+            C = gen.make_instance(fam, 90, seed=budget)
+            u, v = mintrick_seeds(C, rng)
+            _check_seeded(lib, C, u, v, (fam, budget))
+            u, v = noisy_oracle_seeds(C, 1e-2)
+            _check_seeded(lib, C, u, v, (fam, budget, "noisy"))
+    _opt(lib, ctx, "solver_smem_budget", 0)
+    _opt(lib, ctx, "solver_threads", 0)
+
+
 def test_non_fp32_matrix_takes_the_binary64_path(emu):
     lib, ctx = emu
     rng = np.random.default_rng(5)
