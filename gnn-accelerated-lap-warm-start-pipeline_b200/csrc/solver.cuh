@@ -26,10 +26,14 @@
 
 namespace b200lap {
 
-constexpr int kTraceWords = 12;
+constexpr int kTraceWords = 20;
 enum TraceSlot {
     TR_PROJ = 0, TR_TIGHT = 1, TR_GREEDY = 2, TR_FALLBACK = 3, TR_MICRO = 4, TR_FREE_CR = 5,
-    TR_ARR = 6, TR_PATHS = 7, TR_COLLECT = 8, TR_RELAX = 9, TR_RC = 10, TR_SPARE = 11
+    TR_ARR = 6, TR_PATHS = 7, TR_COLLECT = 8, TR_RELAX = 9, TR_RC = 10,
+    // SM-clock cycles spent (thread 0's view) in: relax steps, collect steps, ARR row scans + reductions, ARR serial updates, total
+    TR_CYC_RELAX = 11, TR_CYC_COLLECT = 12, TR_CYC_ARR_SCAN = 13, TR_CYC_ARR_SERIAL = 14, TR_CYC_TOTAL = 15,
+    // records replayed by collect steps, cycles of the serial replays (warp 0), hits replayed by relax steps
+    TR_RECORDS = 16, TR_CYC_COLLECT_REPLAY = 17, TR_CYC_RELAX_REPLAY = 18, TR_RELAX_HITS = 19
 };
 
 struct SolverShared {
@@ -40,7 +44,7 @@ struct SolverShared {
     int hi, final_j, next_row, aux;
     int minw[3], maxw[3];   // hit-word ranges, rotated over 3 steps (reset one step after use)
     unsigned int cursor, deferred;
-    int hitk[32];           // positions of the flagged records of a collect step, ascending
+    int hitk[64];           // positions of the flagged records of a collect step, ascending
     long long tr[kTraceWords];
 };
 
@@ -108,6 +112,14 @@ template <typename CT> struct SolverCtx {
     int step;   // relax/collect step counter (selects the minw/maxw slot)
 };
 
+__device__ __forceinline__ long long sm_clock() {
+#ifdef B200LAP_EMUL
+    return 0;
+#else
+    return clock64();
+#endif
+}
+
 // ---- one thread-strided pass over a matrix row ----------------------------------------------------
 // With MAXC > 0 (blockDim.x * MAXC >= n) the thread's entries are loaded into registers FIRST, as
 // independent coalesced loads, and only then handed to `body` -- a row costs one memory latency, not
@@ -142,15 +154,14 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
 {
     // executed by warp 0 only
     const int lane = lane_id();
+    const long long t0 = sm_clock();
     int hi = lo;
     double level = INFINITY;
-    bool done = false;
-    if (whi - wlo < 32) {
-        // Common case (a handful of prefix-minimum records): enumerate the set bits into lanes, fetch
-        // (position, column, distance) of every record IN PARALLEL -- they are not touched by the swaps
-        // of earlier records -- and leave only the cols[hi] read on lane 0's serial chain.
-        unsigned int bits = 0;
-        if (wlo + lane <= whi) { bits = S.bitmap[wlo + lane]; S.bitmap[wlo + lane] = 0u; }
+    // 1) enumerate the flagged positions (ascending) into hitk[]: all lanes work, 32 words per round
+    int total = 0;
+    bool overflow = false;
+    for (int w0 = wlo; w0 <= whi; w0 += 32) {
+        const unsigned int bits = (w0 + lane <= whi) ? S.bitmap[w0 + lane] : 0u;
         const int cnt = __popc(bits);
         int incl = cnt;
 #pragma unroll
@@ -158,20 +169,28 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
             const int t = __shfl_up_sync(kFull, incl, o);
             if (lane >= o) incl += t;
         }
-        const int total = __shfl_sync(kFull, incl, 31);
-        if (total <= 32) {
-            int slot = incl - cnt;
-            unsigned int w = bits;
-            while (w) {
-                const int bpos = __ffs((int)w) - 1;
-                w &= w - 1;
-                S.sh->hitk[slot++] = (wlo + lane) * 32 + bpos;
-            }
-            __syncwarp();
+        const int round_total = __shfl_sync(kFull, incl, 31);
+        if (total + round_total > 64) { overflow = true; break; }
+        int slot = total + incl - cnt;
+        unsigned int w = bits;
+        while (w) {
+            const int bpos = __ffs((int)w) - 1;
+            w &= w - 1;
+            S.sh->hitk[slot++] = (w0 + lane) * 32 + bpos;
+        }
+        total += round_total;
+    }
+    __syncwarp();
+    if (!overflow) {
+        // 2) fetch (position, column, distance) of every record IN PARALLEL -- none of them is touched by the
+        //    swaps of earlier records -- and leave only the cols[hi] read on lane 0's serial chain
+        for (int w = wlo + lane; w <= whi; w += 32) S.bitmap[w] = 0u;
+        for (int base = 0; base < total; base += 32) {
+            const int cnt = min(32, total - base);
             int my_k = 0, my_j = 0;
             double my_d = INFINITY;
-            if (lane < total) { my_k = S.sh->hitk[lane]; my_j = S.cols[my_k]; my_d = S.d[my_j]; }
-            for (int h = 0; h < total; ++h) {
+            if (lane < cnt) { my_k = S.sh->hitk[base + lane]; my_j = S.cols[my_k]; my_d = S.d[my_j]; }
+            for (int h = 0; h < cnt; ++h) {
                 const int k = __shfl_sync(kFull, my_k, h);
                 const int j = __shfl_sync(kFull, my_j, h);
                 const double dj = __shfl_sync(kFull, my_d, h);
@@ -183,36 +202,36 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
                     ++hi;
                 }
             }
-            done = true;
-        } else {
-            // put the words back for the general path below
-            if (wlo + lane <= whi) S.bitmap[wlo + lane] = bits;
-            __syncwarp();
         }
-    }
-    for (int w0 = wlo; !done && w0 <= whi; w0 += 32) {
-        unsigned int bits = 0;
-        if (w0 + lane <= whi) { bits = S.bitmap[w0 + lane]; S.bitmap[w0 + lane] = 0u; }
-        unsigned int nz = __ballot_sync(kFull, bits != 0u);
-        while (nz) {
-            const int l = __ffs((int)nz) - 1;
-            nz &= nz - 1;
-            unsigned int word = __shfl_sync(kFull, bits, l);
-            if (lane == 0) {
-                while (word) {
-                    const int bpos = __ffs((int)word) - 1;
-                    word &= word - 1;
-                    const int k = (w0 + l) * 32 + bpos;
-                    const int j = S.cols[k];
-                    const double dj = S.d[j];
-                    if (dj < level) { hi = lo; level = dj; }
-                    const int c2 = S.cols[hi];
-                    S.cols[k] = c2; S.pos[c2] = k;
-                    S.cols[hi] = j; S.pos[j] = hi;
-                    ++hi;
+    } else {
+        // tie-heavy level (more than 64 records): plain serial walk over the bitmap
+        total = 0;
+        for (int w0 = wlo; w0 <= whi; w0 += 32) {
+            unsigned int bits = 0;
+            if (w0 + lane <= whi) { bits = S.bitmap[w0 + lane]; S.bitmap[w0 + lane] = 0u; }
+            unsigned int nz = __ballot_sync(kFull, bits != 0u);
+            while (nz) {
+                const int l = __ffs((int)nz) - 1;
+                nz &= nz - 1;
+                unsigned int word = __shfl_sync(kFull, bits, l);
+                if (lane == 0) {
+                    while (word) {
+                        const int bpos = __ffs((int)word) - 1;
+                        word &= word - 1;
+                        const int k = (w0 + l) * 32 + bpos;
+                        const int j = S.cols[k];
+                        const double dj = S.d[j];
+                        if (dj < level) { hi = lo; level = dj; }
+                        const int c2 = S.cols[hi];
+                        S.cols[k] = c2; S.pos[c2] = k;
+                        S.cols[hi] = j; S.pos[j] = hi;
+                        ++hi;
+                        ++total;
+                    }
                 }
             }
         }
+        total = __shfl_sync(kFull, total, 0);
     }
     hi = __shfl_sync(kFull, hi, 0);
     if (hi == lo) hi = lo + 1;   // only reachable with NaN distances; keep moving
@@ -225,6 +244,8 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
     if (lane == 0) {
         S.sh->hi = hi;
         S.sh->final_j = best >= 0 ? S.cols[best] : -1;
+        S.sh->tr[TR_RECORDS] += total;
+        S.sh->tr[TR_CYC_COLLECT_REPLAY] += sm_clock() - t0;
     }
 }
 
@@ -232,6 +253,7 @@ template <typename CT>
 __device__ __forceinline__ void replay_relax(SolverCtx<CT>& S, int hi_in, int wlo, int whi)
 {
     const int lane = lane_id();
+    const long long t0 = sm_clock();
     int hi = hi_in, fin = -1;
     for (int w0 = wlo; w0 <= whi; w0 += 32) {
         unsigned int bits = 0;
@@ -256,7 +278,7 @@ __device__ __forceinline__ void replay_relax(SolverCtx<CT>& S, int hi_in, int wl
             }
         }
     }
-    if (lane == 0) { S.sh->hi = hi; S.sh->final_j = fin; }
+    if (lane == 0) { S.sh->hi = hi; S.sh->final_j = fin; S.sh->tr[TR_RELAX_HITS] += hi - hi_in + (fin >= 0); S.sh->tr[TR_CYC_RELAX_REPLAY] += sm_clock() - t0; }
 }
 
 // ---- one shortest augmenting path (find_path_dense) ---------------------------------------------
@@ -277,6 +299,7 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
     while (final_j < 0) {
         if (lo == hi) {
             // ---- level collect: positions [lo, n) in blocked ownership, prefix-min records flagged
+            const long long tc0 = sm_clock();
             n_ready = lo;
             const int L = n - lo;
             const int chunk = (L + T - 1) / T;
@@ -347,8 +370,10 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
             S.step++;
             hi = sh->hi;
             final_j = sh->final_j;
+            if (tid == 0) sh->tr[TR_CYC_COLLECT] += sm_clock() - tc0;
         }
         // ---- relax from every SCAN column in turn (_scan_dense)
+        const long long tr0 = sm_clock();
         while (final_j < 0 && lo != hi) {
             const int js = S.cols[lo];
             const int i = S.y[js];
@@ -420,6 +445,7 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                 final_j = sh->final_j;
             }
         }
+        if (tid == 0) sh->tr[TR_CYC_RELAX] += sm_clock() - tr0;
     }
     // ---- dual update of the READY columns (lapjv.cpp:270-276); lo of the caller == n_ready
     const double level = S.d[S.cols[n_ready]];
@@ -525,6 +551,7 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
     __syncthreads();
     while (cursor < (unsigned int)n_free) {
         ++steps;
+        const long long ta0 = sm_clock();
         const int r = S.free_rows[cursor++];
         const CT* crow = S.C + (size_t)r * S.ld;
         const double c0 = (double)__ldg(crow) - S.v[0];
@@ -561,8 +588,10 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
         }
         k1 = t.i1; b1 = t.a1;
         if (t.i2 == 0x7fffffff) { k2 = -1; b2 = B200LAP_LARGE; } else { k2 = t.i2; b2 = t.a2; }
+        const long long ta1 = sm_clock();
         if (tid == 0) {
             sh->tr[TR_ARR]++;
+            sh->tr[TR_CYC_ARR_SCAN] += ta1 - ta0;
             int owner = S.y[k1];
             const double lowered = S.v[k1] - (b2 - b1);
             const bool does_lower = lowered < S.v[k1];
@@ -586,6 +615,7 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
             sh->deferred = (unsigned int)deferred;
         }
         __syncthreads();
+        if (tid == 0) sh->tr[TR_CYC_ARR_SERIAL] += sm_clock() - ta1;
         cursor = sh->cursor;
         deferred = (int)sh->deferred;
     }
@@ -649,6 +679,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     const CT* colmin = a.colmin + (size_t)b * n;
     const int* colarg = a.colarg + (size_t)b * n;
     int rc = 0;
+    const long long t_start = sm_clock();
     __syncthreads();
 
     if (a.mode == 1) {
@@ -765,6 +796,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     if (tid == 0) {
         a.rc[b] = rc;
         sh.tr[TR_RC] = rc;
+        sh.tr[TR_CYC_TOTAL] = sm_clock() - t_start;
         if (a.trace)
             for (int q = 0; q < kTraceWords; ++q) a.trace[(size_t)b * kTraceWords + q] = sh.tr[q];
     }

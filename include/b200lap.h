@@ -21,7 +21,7 @@ extern "C" {
 #define B200LAP_ERR_ARG (-102)
 
 #define B200LAP_ROW_FEAT_DIM 21   /* gnn/features.py:223-241 */
-#define B200LAP_TRACE_WORDS 12
+#define B200LAP_TRACE_WORDS 20
 #define B200LAP_TOPK_MAX 32
 
 typedef struct b200lap_ctx b200lap_ctx;       /* one per (device, stream): workspaces + stream */
@@ -43,7 +43,9 @@ int b200lap_lapjv(const double* C, int n, int* x, int* y);
 /* Batched host entry: `batch` independent instances, C [batch][n][n], seeds [batch][n].
  * rc[batch] receives each instance's lapjv_seeded return code; trace (nullable)
  * [batch][B200LAP_TRACE_WORDS] the phase counters (proj_triggers, tight_edges, greedy_matched,
- * took_fallback, micro_bumps, free_after_cr, arr_iters, aug_paths, collect_calls, relax_cols, rc, -). */
+ * took_fallback, micro_bumps, free_after_cr, arr_iters, aug_paths, collect_calls, relax_cols, rc, then SM-clock
+ * cycles spent in relax steps, collect steps, ARR scans, ARR serial updates, the whole solve; collect records,
+ * cycles of the serial collect / relax replays, relax hits). */
 int b200lap_lapjv_seeded_batch(const double* C, int batch, int n, long long* x, long long* y,
                                const double* u_seed, const double* v_seed, double eps, int* rc,
                                long long* trace);
@@ -89,7 +91,7 @@ int b200lap_dev_predict_duals(b200lap_ctx* ctx, const b200lap_model* model, cons
 
 /* ------------------------------------------------------------------------------------------
  * 4. Solver half on DEVICE buffers (same matrix conventions).  x,y int32 [batch][n] (written
- *    for instances with rc == 0), rc int32 [batch], trace int64 [batch][12] nullable,
+ *    for instances with rc == 0), rc int32 [batch], trace int64 [batch][20] nullable,
  *    v_out binary64 [batch][n] nullable (final column potentials).
  * ------------------------------------------------------------------------------------------ */
 int b200lap_dev_solve_seeded(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const double* u_seed,
