@@ -13,6 +13,7 @@
 #include "frontend.cuh"
 #include "solver.cuh"
 #include "features.cuh"
+#include "features_smem.cuh"
 #include "mlp.cuh"
 #include "mlp_tc.cuh"
 #include "../../include/b200lap.h"
@@ -58,6 +59,14 @@ struct b200lap_ctx {
     int front_rows_per_cta = 0;  // option
     int mlp_impl = 0;            // option: 0 = default
     int feat_ept = 0;            // option: entries per thread of the row-feature kernel (0 = auto)
+    int feat_impl = 0;           // option: 0 = shared-memory streaming kernel for binary32 storage, 1 = register-resident kernel
+    int feat_threads = 0;        // options of the streaming kernel (0 = auto): CTA size, row buffers, sample size, CTAs per SM
+    int feat_nbuf = 0;
+    int feat_nsamp = 0;
+    int feat_ctas = 0;
+    int sm_count = 148;
+    float* posenc = nullptr;     // cached positional-encoding table [posenc_n][8]
+    int posenc_n = 0;
     std::mutex mu;
 
     void ws_reset() {
@@ -332,6 +341,12 @@ int b200lap_ctx_create(int device, void* stream, b200lap_ctx** out) {
     b200lap_ctx* c = new (std::nothrow) b200lap_ctx();
     if (!c) return fail(-1, "host allocation failed");
     c->device = device;
+#ifndef B200LAP_EMUL
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->sm_count = sms;
+    }
+#endif
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
@@ -348,6 +363,7 @@ void b200lap_ctx_destroy(b200lap_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->blocks) cudaFree(b.p);
+    if (ctx->posenc) cudaFree(ctx->posenc);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -371,6 +387,11 @@ int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value) {
     else if (k == "front_rows_per_cta") ctx->front_rows_per_cta = (int)value;
     else if (k == "mlp_impl") ctx->mlp_impl = (int)value;
     else if (k == "feat_ept") ctx->feat_ept = (int)value;
+    else if (k == "feat_impl") ctx->feat_impl = (int)value;
+    else if (k == "feat_threads") ctx->feat_threads = (int)value;
+    else if (k == "feat_nbuf") ctx->feat_nbuf = (int)value;
+    else if (k == "feat_nsamp") ctx->feat_nsamp = (int)value;
+    else if (k == "feat_ctas") ctx->feat_ctas = (int)value;
     else return fail(B200LAP_ERR_ARG, "unknown option " + k);
     return 0;
 }

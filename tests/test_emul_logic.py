@@ -186,3 +186,69 @@ def test_front_end_flags(emu):
     # infeasible seeds are reported by the sweep (and repaired later by the solver's projection)
     assert lib.b200lap_dev_front_end(ctx, C.ctypes.data, 0, 1, n, (u + 1).ctypes.data, v.ctypes.data, 1e-12, ut.ctypes.data, tc.ctypes.data, fl.ctypes.data) == 0
     assert fl[0] == 1 and fl[1] == 1
+
+
+def _feat_cases():
+    rng = np.random.default_rng(77)
+    out = {}
+    out["uniform96"] = rng.uniform(0, 1, (96, 96))
+    sp = rng.uniform(0, 1, (100, 100))
+    sp[rng.uniform(size=sp.shape) > 0.3] = 1e6
+    out["sparse200"] = sp
+    out["clustered64"] = gen.generate_clustered_costs(64, seed=3)
+    out["odd67"] = rng.uniform(0, 100, (67, 67))
+    out["even66"] = rng.normal(50, 10, (66, 66))             # isolated row minima: ill-conditioned entropy
+    pat = np.zeros((64, 64))
+    pat[0] = 3.25                                            # constant row
+    pat[1] = np.where(np.arange(64) < 32, 0.0, 1.0)          # two values: the median straddles them
+    pat[2] = np.arange(64)                                   # sorted
+    pat[3] = np.arange(64)[::-1] * 0.5                       # reverse sorted
+    pat[4] = np.arange(64) % 4                               # periodic
+    pat[5] = 1000.0; pat[5, 17] = 0.0                        # one low outlier
+    pat[6] = rng.integers(0, 3, 64)                          # heavy ties around the median
+    pat[7] = np.where(np.arange(64) % 2 == 0, 5.0, rng.uniform(4.9, 5.1, 64))   # half the row tied AT the median
+    pat[8:] = rng.uniform(0, 1, (56, 64))
+    pat[8:, :3] = 0.0                                        # ties at the minimum (top-k of equal values)
+    out["patterns64"] = pat
+    for k in (1, 2, 3, 5, 12):
+        out[f"tiny{k}"] = rng.uniform(0, 1, (k, k))
+    return {k: v.astype(np.float32).astype(np.float64) for k, v in out.items()}
+
+
+def test_row_features_streaming_kernel(emu):
+    """The shared-memory streaming row-feature kernel (features_smem.cuh) against the NumPy oracle: both
+    load variants, tie mode, list overflow / bracket-miss fall-backs (forced with a tiny sample), all
+    CTA sizes.  The order statistics are exact; the stated tolerance is 1e-4."""
+    from oracle import features_np
+    lib, ctx = emu
+    cases = _feat_cases()
+    configs = [dict(), dict(feat_threads=128, feat_nbuf=1, feat_nsamp=40), dict(feat_nsamp=8, feat_threads=64)]
+    try:
+        for name, C in cases.items():
+            n = C.shape[0]
+            ref = features_np.row_features(C)
+            srt = np.sort(C.astype(np.float32), axis=1)
+            for ci, cfg in enumerate(configs):
+                if ci == 1 and n < 60:
+                    continue
+                for k in ("feat_threads", "feat_nbuf", "feat_nsamp"):
+                    _opt(lib, ctx, k, cfg.get(k, 0))
+                topk = 16
+                B = 2 if name == "uniform96" else 1
+                Cf = np.ascontiguousarray(np.stack([C, C[::-1].copy()])[:B], dtype=np.float32)
+                feat = np.zeros((B, n, 21), np.float32)
+                topv = np.zeros((B, n, topk), np.float32)
+                assert lib.b200lap_dev_row_features(ctx, Cf.ctypes.data, 0, B, n, topk, None, feat.ctypes.data, topv.ctypes.data) == 0, (name, cfg)
+                try:
+                    feature_close(feat[0], ref, rtol=1e-4)
+                except AssertionError as e:
+                    raise AssertionError(f"{name} {cfg}: {e}")
+                ks = min(topk, n)
+                assert np.array_equal(topv[0][:, :ks], srt[:, :ks]), (name, cfg)
+                assert np.all(np.isinf(topv[0][:, ks:]))
+                # second instance of the batch = the same rows in reverse order: row statistics move with the rows
+                if B == 2:
+                    feature_close(feat[1], features_np.row_features(C[::-1].copy()), rtol=1e-4)
+    finally:
+        for k in ("feat_threads", "feat_nbuf", "feat_nsamp"):
+            _opt(lib, ctx, k, 0)

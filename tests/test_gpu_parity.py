@@ -202,6 +202,53 @@ def test_row_features_match_golden(golden, fam):
     feature_close(f, golden[f"{fam}/feat"], rtol=1e-4)
 
 
+def _pattern_rows(n, rng):
+    """Rows built to defeat a sampled bracket: ties at / around the median, sorted and periodic rows, outliers."""
+    P = rng.uniform(0, 1, (n, n))
+    j = np.arange(n)
+    P[0] = 3.25
+    P[1] = np.where(j < n // 2, 0.0, 1.0)
+    P[2] = j
+    P[3] = j[::-1] * 0.5
+    P[4] = j % 4
+    P[5] = 1000.0; P[5, n // 3] = 0.0
+    P[6] = rng.integers(0, 3, n)
+    P[7] = np.where(j % 2 == 0, 5.0, rng.uniform(4.9, 5.1, n))
+    P[8] = np.where(j % (n // 512 if n >= 1024 else 2) == 0, rng.uniform(0, 1, n), 7.0)      # period == the sample stride
+    P[9] = rng.normal(50, 10, n)                                                           # isolated minimum: entropy ~ 0
+    P[10] = np.exp(rng.normal(0, 4, n))                                                    # heavy tail: one histogram bin holds almost all
+    P[11:40, :5] = 0.0                                                                     # ties at the row minimum
+    return gen.snap_to_fp32_grid(P)
+
+
+@pytest.mark.parametrize("n,opts", [(64, {}), (516, {}), (1030, {}), (2048, {}), (2048, {"feat_nbuf": 1, "feat_threads": 256}),
+                                    (2048, {"feat_nsamp": 16}), (4096, {}), (8192, {"feat_threads": 512}), (16384, {})])
+def test_streaming_row_features_patterns_and_options(ctx, n, opts):
+    """features_smem.cuh on adversarial rows and non-default launch shapes (tiny sample => the bracket misses and
+    the exact whole-row fall-back runs).  Order statistics exact, floating features within 1e-4."""
+    import torch
+    rng = np.random.default_rng(n)
+    C = _pattern_rows(n, rng)
+    rows = np.r_[0:40, n - 8:n] if n > 2048 else np.arange(n)
+    ref = features_np.row_features(C)[rows] if n <= 2048 else None
+    if ref is None:
+        full = features_np.row_features(C[rows])          # row statistics of the chosen rows ...
+        colmin = C.min(axis=0)
+        full[:, 12] = (C[rows] == colmin[None, :]).mean(axis=1)                 # ... is_col_best needs all rows
+        full[:, 13:] = features_np.positional_terms(n)[rows]
+        ref = full
+    try:
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        feat, topv = ctx.row_features(torch.from_numpy(C.astype(np.float32)).cuda(), topk=16)
+        ctx.sync()
+    finally:
+        for k in opts:
+            ctx.set_option(k, 0)
+    feature_close(feat[0].cpu().numpy()[rows], ref, rtol=1e-4)
+    assert np.array_equal(topv[0].cpu().numpy()[rows], np.sort(C[rows].astype(np.float32), axis=1)[:, :16])
+
+
 @pytest.mark.parametrize("fam", FAMILIES)
 @pytest.mark.parametrize("n", [100, 512, 1030, 2048])
 def test_row_features_match_numpy_definition(ctx, fam, n):
