@@ -50,7 +50,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, os.path.join(CSRC, "api.cu")]
+    prof = ["-DB200LAP_SOLVER_PROFILE"] if os.environ.get("B200LAP_PROFILE") == "1" else []   # cycle counters in the solver trace
+    cmd = [nvcc_path()] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, os.path.join(CSRC, "api.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

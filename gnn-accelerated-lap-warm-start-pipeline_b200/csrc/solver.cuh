@@ -112,13 +112,16 @@ template <typename CT> struct SolverCtx {
     int step;   // relax/collect step counter (selects the minw/maxw slot)
 };
 
-__device__ __forceinline__ long long sm_clock() {
-#ifdef B200LAP_EMUL
-    return 0;
+// Cycle-level phase counters (trace words 11..19) are compiled in only with -DB200LAP_SOLVER_PROFILE
+// (B200LAP_PROFILE=1 python build.py; tools/solver_breakdown.py): their shared-memory read-modify-writes sit on
+// the serial chain of every step.  Without the macro those trace words stay zero.
+#if defined(B200LAP_SOLVER_PROFILE) && !defined(B200LAP_EMUL)
+#define B200LAP_PROF(stmt) do { stmt; } while (0)
+__device__ __forceinline__ long long sm_clock() { return clock64(); }
 #else
-    return clock64();
+#define B200LAP_PROF(stmt) do { } while (0)
+__device__ __forceinline__ long long sm_clock() { return 0; }
 #endif
-}
 
 // ---- one thread-strided pass over a matrix row ----------------------------------------------------
 // With MAXC > 0 (blockDim.x * MAXC >= n) the thread's entries are loaded into registers FIRST, as
@@ -244,8 +247,7 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
     if (lane == 0) {
         S.sh->hi = hi;
         S.sh->final_j = best >= 0 ? S.cols[best] : -1;
-        S.sh->tr[TR_RECORDS] += total;
-        S.sh->tr[TR_CYC_COLLECT_REPLAY] += sm_clock() - t0;
+        B200LAP_PROF(S.sh->tr[TR_RECORDS] += total; S.sh->tr[TR_CYC_COLLECT_REPLAY] += sm_clock() - t0);
     }
 }
 
@@ -278,7 +280,10 @@ __device__ __forceinline__ void replay_relax(SolverCtx<CT>& S, int hi_in, int wl
             }
         }
     }
-    if (lane == 0) { S.sh->hi = hi; S.sh->final_j = fin; S.sh->tr[TR_RELAX_HITS] += hi - hi_in + (fin >= 0); S.sh->tr[TR_CYC_RELAX_REPLAY] += sm_clock() - t0; }
+    if (lane == 0) {
+        S.sh->hi = hi; S.sh->final_j = fin;
+        B200LAP_PROF(S.sh->tr[TR_RELAX_HITS] += hi - hi_in + (fin >= 0); S.sh->tr[TR_CYC_RELAX_REPLAY] += sm_clock() - t0);
+    }
 }
 
 // ---- one shortest augmenting path (find_path_dense) ---------------------------------------------
@@ -370,7 +375,7 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
             S.step++;
             hi = sh->hi;
             final_j = sh->final_j;
-            if (tid == 0) sh->tr[TR_CYC_COLLECT] += sm_clock() - tc0;
+            B200LAP_PROF(if (tid == 0) sh->tr[TR_CYC_COLLECT] += sm_clock() - tc0);
         }
         // ---- relax from every SCAN column in turn (_scan_dense)
         const long long tr0 = sm_clock();
@@ -445,7 +450,7 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                 final_j = sh->final_j;
             }
         }
-        if (tid == 0) sh->tr[TR_CYC_RELAX] += sm_clock() - tr0;
+        B200LAP_PROF(if (tid == 0) sh->tr[TR_CYC_RELAX] += sm_clock() - tr0);
     }
     // ---- dual update of the READY columns (lapjv.cpp:270-276); lo of the caller == n_ready
     const double level = S.d[S.cols[n_ready]];
@@ -591,7 +596,7 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
         const long long ta1 = sm_clock();
         if (tid == 0) {
             sh->tr[TR_ARR]++;
-            sh->tr[TR_CYC_ARR_SCAN] += ta1 - ta0;
+            B200LAP_PROF(sh->tr[TR_CYC_ARR_SCAN] += ta1 - ta0);
             int owner = S.y[k1];
             const double lowered = S.v[k1] - (b2 - b1);
             const bool does_lower = lowered < S.v[k1];
@@ -615,7 +620,7 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
             sh->deferred = (unsigned int)deferred;
         }
         __syncthreads();
-        if (tid == 0) sh->tr[TR_CYC_ARR_SERIAL] += sm_clock() - ta1;
+        B200LAP_PROF(if (tid == 0) sh->tr[TR_CYC_ARR_SERIAL] += sm_clock() - ta1);
         cursor = sh->cursor;
         deferred = (int)sh->deferred;
     }
@@ -796,7 +801,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     if (tid == 0) {
         a.rc[b] = rc;
         sh.tr[TR_RC] = rc;
-        sh.tr[TR_CYC_TOTAL] = sm_clock() - t_start;
+        B200LAP_PROF(sh.tr[TR_CYC_TOTAL] = sm_clock() - t_start);
         if (a.trace)
             for (int q = 0; q < kTraceWords; ++q) a.trace[(size_t)b * kTraceWords + q] = sh.tr[q];
     }
