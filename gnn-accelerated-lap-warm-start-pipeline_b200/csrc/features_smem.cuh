@@ -252,6 +252,21 @@ struct ListCursor {
 #endif
 };
 
+// Walk of a thread-private list through its 32-bit shared-window address (LDS + IADD + compare per key).
+#ifdef B200LAP_EMUL
+template <typename F> __device__ __forceinline__ void walk_list(const ListCursor& c, F f) {
+    for (const float* q = c.p0; q != c.p; q += c.step) f(*q);
+}
+#else
+template <typename F> __device__ __forceinline__ void walk_list(const ListCursor& c, F f) {
+    for (uint32_t q = c.a0; q != c.a; q += c.step) {
+        float x;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(q));
+        f(x);
+    }
+}
+#endif
+
 // Upper end of the histogram range of a list admitted by fl(c - L) <= w.  A key a rounding above it lands in the
 // last bin (sel_bin256_in clamps), and both list passes use the same bin function, so it need not be exact.
 __device__ __forceinline__ float bracket_upper(float L, float w) { return L + w * 1.0001f; }
@@ -301,9 +316,13 @@ __device__ __forceinline__ void bracket_fast(FeatSmemFixed& F, const float* samp
     for (int level = 0;; ++level) {
         if (!(lo < hi)) { L = lo; H = lo; return; }
         const float scale = (float)kSelBins / (hi - lo);
-        for (int i = tid; i < s; i += T) {
-            const float x = samp[i];
-            if (x >= lo && x <= hi) atomicAdd(&h[sel_bin256(x, lo, scale)], 1);
+        if (level == 0) {
+            for (int i = tid; i < s; i += T) atomicAdd(&h[sel_bin256_in(samp[i], lo, scale)], 1);   // every key is inside [lo, hi]
+        } else {
+            for (int i = tid; i < s; i += T) {
+                const float x = samp[i];
+                if (x >= lo && x <= hi) atomicAdd(&h[sel_bin256(x, lo, scale)], 1);
+            }
         }
         __syncthreads();
         if (warp_id() == 0) {
@@ -541,7 +560,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_row_features_smem(FeatSmemArgs a
         // ---- median
         auto ident = [](float x) { return x; };
         auto each_row_raw = [&](auto f) { each_row(ident, f); };
-        auto each_list = [&](auto f) { for (int k = 0, q = tid; k < mycnt; ++k, q += T) f(list[q]); };
+        auto each_list = [&](auto f) { walk_list(cur, f); };
         float med_f;
         double med;
         {
@@ -732,7 +751,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_row_features_smem(FeatSmemArgs a
             float da = L2, db2 = L2;
             bool tiny_pending = false;
             int k1 = 0, k2 = 0, cnt = 0;
-            auto each_list_abs = [&](auto f) { for (int k = 0, q = tid; k < mycnt; ++k, q += T) f(fabsf(list[q])); };
+            auto each_list_abs = [&](auto f) { walk_list(cur, [&](float x) { f(fabsf(x)); }); };
             if (ok && !tie2) {
                 const float Hb = bracket_upper(L2, H2 - L2);
                 const float scale = (float)kSelBins / (Hb - L2);

@@ -287,7 +287,7 @@ __device__ __forceinline__ void replay_relax(SolverCtx<CT>& S, int hi_in, int wl
 }
 
 // ---- one shortest augmenting path (find_path_dense) ---------------------------------------------
-template <int MAXC, typename CT>
+template <int MAXC, bool SMALLREG, typename CT>
 __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
 {
     const int n = S.n, T = blockDim.x, tid = threadIdx.x;
@@ -407,24 +407,30 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                 // every load of the step (matrix row AND the thread's pos/v/d entries) is issued before the
                 // first dependent instruction: the compiler cannot hoist shared loads over the stores of the
                 // previous column by itself, and a column-at-a-time body costs ~700 cycles per column
+                // The matrix-row loads (the long latency) are all in flight at once; the thread's pos/v/d entries
+                // follow in groups of CH columns so that the 64-register variants (1024 threads) do not spill.
+                constexpr int CH = SMALLREG ? (MAXC < 4 ? MAXC : 4) : (MAXC < 8 ? MAXC : 8);
                 CT cr[MAXC];
-                int kq[MAXC];
-                double vq[MAXC], dq[MAXC];
 #pragma unroll
                 for (int q = 0; q < MAXC; ++q) {
                     const int j = tid + q * T;
                     cr[q] = j < n ? __ldg(crow + j) : (CT)0;
                 }
-#pragma unroll
-                for (int q = 0; q < MAXC; ++q) {
-                    const int j = tid + q * T;
-                    kq[q] = j < n ? S.pos[j] : -1;
-                    vq[q] = j < n ? S.v[j] : 0.0;
-                    dq[q] = j < n ? S.d[j] : 0.0;
-                }
                 const double slack = ((double)c_js - v_js) - level;
 #pragma unroll
-                for (int q = 0; q < MAXC; ++q) relax_one(tid + q * T, kq[q], (double)cr[q], vq[q], dq[q], slack);
+                for (int q0 = 0; q0 < MAXC; q0 += CH) {
+                    int kq[CH];
+                    double vq[CH], dq[CH];
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) {
+                        const int j = tid + (q0 + q) * T;
+                        kq[q] = j < n ? S.pos[j] : -1;
+                        vq[q] = j < n ? S.v[j] : 0.0;
+                        dq[q] = j < n ? S.d[j] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) relax_one(tid + (q0 + q) * T, kq[q], (double)cr[q0 + q], vq[q], dq[q], slack);
+                }
             } else {
                 const double slack = ((double)c_js - v_js) - level;
                 for (int j = tid; j < n; j += T) relax_one(j, S.pos[j], (double)crow[j], S.v[j], S.d[j], slack);
@@ -459,12 +465,12 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
     return final_j;
 }
 
-template <int MAXC, typename CT>
+template <int MAXC, bool SMALLREG, typename CT>
 __device__ void augment_all(SolverCtx<CT>& S, int n_free)
 {
     for (int f = 0; f < n_free; ++f) {
         const int root = S.free_rows[f];
-        int col = shortest_path<MAXC>(S, root);
+        int col = shortest_path<MAXC, SMALLREG>(S, root);
         __syncthreads();
         if (threadIdx.x == 0) {
             S.sh->tr[TR_PATHS]++;
@@ -627,14 +633,14 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
     return deferred;
 }
 
-template <int MAXC, typename CT>
+template <int MAXC, bool SMALLREG, typename CT>
 __device__ void cold_solve(SolverCtx<CT>& S, const CT* colmin, const int* colarg)
 {
     int left = col_reduce<MAXC>(S, colmin, colarg);
     if (threadIdx.x == 0) S.sh->tr[TR_FREE_CR] = left;
     for (int pass = 0; left > 0 && pass < 2; ++pass) left = arr_pass<MAXC>(S, left);
     __syncthreads();
-    if (left > 0) augment_all<MAXC>(S, left);
+    if (left > 0) augment_all<MAXC, SMALLREG>(S, left);
 }
 
 // ---- the persistent per-instance kernel -----------------------------------------------------------
@@ -688,7 +694,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     __syncthreads();
 
     if (a.mode == 1) {
-        cold_solve<MAXC>(S, colmin, colarg);
+        cold_solve<MAXC, (MAXT > 512)>(S, colmin, colarg);
     } else {
         const double eps = a.eps;
         const double tol = eps > 1e-9 ? eps : 1e-9;
@@ -769,7 +775,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
             if ((double)(long long)tight < 1.2 * n) {
                 if (tid == 0) sh.tr[TR_FALLBACK] = 1;
                 __syncthreads();
-                cold_solve<MAXC>(S, colmin, colarg);
+                cold_solve<MAXC, (MAXT > 512)>(S, colmin, colarg);
             } else if (n_free > 0) {
                 // ---- micro-ARR (lapjv_seeded.cpp:136-159); "j1 in free_cols" == y[j1] < 0 after greedy
                 for (int f = 0; f < n_free; ++f) {
@@ -786,7 +792,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
                     }
                     __syncthreads();
                 }
-                augment_all<MAXC>(S, n_free);
+                augment_all<MAXC, (MAXT > 512)>(S, n_free);
             }
         }
     }
