@@ -150,21 +150,47 @@ __device__ __forceinline__ void top2_merge(Top2& t, const Top2& o) {
     top2_push(t, o.a1, o.i1);
     top2_push(t, o.a2, o.i2);
 }
+// for keys pushed in increasing index order (a thread walking its own columns): ties keep the earlier index by themselves
+__device__ __forceinline__ void top2_push_inc(Top2& t, double a, int i) {
+    if (a < t.a1) { t.a2 = t.a1; t.i2 = t.i1; t.a1 = a; t.i1 = i; }
+    else if (a < t.a2) { t.a2 = a; t.i2 = i; }
+}
+// order-preserving 64-bit image of a binary64 value (-0 folded onto +0 first: they compare equal)
+__device__ __forceinline__ unsigned long long d2ord(double x) {
+    const long long b = __double_as_longlong(x + 0.0);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+// lane holding the lexicographic minimum of (a, i) over the warp: three integer redux steps instead of a
+// five-round shuffle butterfly of 64-bit values
+__device__ __forceinline__ int warp_lexmin_lane(double a, int i) {
+    const unsigned long long k = d2ord(a);
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_min_sync(kFull, hi);
+    const bool c1 = hi == mh;
+    const unsigned ml = __reduce_min_sync(kFull, c1 ? lo : 0xffffffffu);
+    const bool c2 = c1 && lo == ml;
+    const unsigned mi = __reduce_min_sync(kFull, c2 ? (unsigned)i : 0xffffffffu);
+    const unsigned who = __ballot_sync(kFull, c2 && (unsigned)i == mi);
+    return __ffs((int)who) - 1;
+}
 __device__ __forceinline__ Top2 warp_top2(Top2 t) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        Top2 q;
-        q.a1 = shfl_xor_d(t.a1, o); q.a2 = shfl_xor_d(t.a2, o);
-        q.i1 = __shfl_xor_sync(kFull, t.i1, o); q.i2 = __shfl_xor_sync(kFull, t.i2, o);
-        top2_merge(t, q);
-    }
-    return t;
+    Top2 r;
+    const int w1 = warp_lexmin_lane(t.a1, t.i1);
+    r.a1 = __shfl_sync(kFull, t.a1, w1);
+    r.i1 = __shfl_sync(kFull, t.i1, w1);
+    if (lane_id() == w1) { t.a1 = t.a2; t.i1 = t.i2; }     // the runner-up is the winner's second or another lane's first
+    const int w2 = warp_lexmin_lane(t.a1, t.i1);
+    r.a2 = __shfl_sync(kFull, t.a1, w2);
+    r.i2 = __shfl_sync(kFull, t.i1, w2);
+    return r;
 }
 
 // ---- a block-reduction scratch with the slot parity kept alongside ----------------------------
 struct BlockRed2 {
     double d2[2][32];
     int i2[2][32];
+    double out_a[2][2];   // block_top2 result (a1, a2) per parity
+    int out_i[2][2];
 };
 struct Red {
     BlockRed* r;
@@ -181,13 +207,29 @@ __device__ __forceinline__ Top2 block_top2(Red& R, Top2 t) {
         R.r2->d2[p][warp_id()] = t.a2; R.r2->i2[p][warp_id()] = t.i2;
     }
     __syncthreads();
-    Top2 q;
-    top2_init(q);
-    if (lane_id() < nw) {
-        q.a1 = R.r->d[p][lane_id()]; q.i1 = R.r->i[p][lane_id()];
-        q.a2 = R.r2->d2[p][lane_id()]; q.i2 = R.r2->i2[p][lane_id()];
+    if (nw == 1) return t;
+    // the cross-warp step is done once, by warp 0, and broadcast (it used to be repeated by every warp)
+    if (warp_id() == 0) {
+        Top2 q;
+        top2_init(q);
+        if (lane_id() < nw) {
+            q.a1 = R.r->d[p][lane_id()]; q.i1 = R.r->i[p][lane_id()];
+            q.a2 = R.r2->d2[p][lane_id()]; q.i2 = R.r2->i2[p][lane_id()];
+        }
+        // first of the union = lexmin of the firsts; second = lexmin of (winner's second, the other firsts)
+        const int w1 = warp_lexmin_lane(q.a1, q.i1);
+        const double a1 = __shfl_sync(kFull, q.a1, w1);
+        const int i1 = __shfl_sync(kFull, q.i1, w1);
+        if (lane_id() == w1) { q.a1 = q.a2; q.i1 = q.i2; }
+        const int w2 = warp_lexmin_lane(q.a1, q.i1);
+        const double a2 = __shfl_sync(kFull, q.a1, w2);
+        const int i2 = __shfl_sync(kFull, q.i1, w2);
+        if (lane_id() == 0) { R.r2->out_a[p][0] = a1; R.r2->out_a[p][1] = a2; R.r2->out_i[p][0] = i1; R.r2->out_i[p][1] = i2; }
     }
-    return warp_top2(q);
+    __syncthreads();
+    Top2 r;
+    r.a1 = R.r2->out_a[p][0]; r.a2 = R.r2->out_a[p][1]; r.i1 = R.r2->out_i[p][0]; r.i2 = R.r2->out_i[p][1];
+    return r;
 }
 __device__ __forceinline__ double red_min_d(Red& R, double v) { return block_min_d(*R.r, R.flip(), v); }
 __device__ __forceinline__ double red_max_d(Red& R, double v) { return block_max_d(*R.r, R.flip(), v); }

@@ -579,7 +579,7 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
         row_scan<MAXC>(crow, n, [&](int j, double c) {
             if (j != 0) {
                 const double red = c - S.v[j];
-                if (red < B200LAP_LARGE) { top2_push(tf, red, j); f = min(f, j); }
+                if (red < B200LAP_LARGE) { top2_push_inc(tf, red, j); f = min(f, j); }
             }
         });
         if (c0 < B200LAP_LARGE) {
@@ -590,7 +590,7 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
             if (f != 0x7fffffff) {
                 if (tid == 0) top2_push(t, c0, 0);
                 row_scan<MAXC>(crow, n, [&](int j, double c) {
-                    if (j >= f) top2_push(t, c - S.v[j], j);
+                    if (j >= f) top2_push_inc(t, c - S.v[j], j);
                 });
             } else if (tid == 0) {
                 top2_push(t, c0, 0);
@@ -784,7 +784,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
                     const double ur = u[r];
                     Top2 t;
                     top2_init(t);
-                    row_scan<MAXC>(crow, n, [&](int j, double c) { top2_push(t, (c - ur) - S.v[j], j); });
+                    row_scan<MAXC>(crow, n, [&](int j, double c) { top2_push_inc(t, (c - ur) - S.v[j], j); });
                     t = block_top2(S.R, t);
                     if (tid == 0 && t.i1 != 0x7fffffff && t.a2 - t.a1 > tol && S.y[t.i1] < 0) {
                         S.v[t.i1] += t.a2 - t.a1;
