@@ -43,6 +43,7 @@ struct SolverShared {
     int s_list[kTightCap];
     int hi, final_j, next_row, aux;
     int minw[3], maxw[3];   // hit-word ranges, rotated over 3 steps (reset one step after use)
+    int nhit[3], hit_k[3], hit_j[3];   // relax steps: number of hits and the first one published (same rotation)
     unsigned int cursor, deferred;
     int hitk[64];           // positions of the flagged records of a collect step, ascending
     long long tr[kTraceWords];
@@ -365,7 +366,7 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                 int wlo = sh->minw[sp], whi = sh->maxw[sp];
                 if (lane_id() == 0) {
                     const int old_slot = (sp + 2) % 3;
-                    sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1;
+                    sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1; sh->nhit[old_slot] = 0;
                     sh->tr[TR_COLLECT]++;
                 }
                 if (whi < 0) { wlo = lo >> 5; whi = wlo; }
@@ -399,6 +400,7 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                             atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
                             wmin_i = min(wmin_i, k >> 5);
                             wmax_i = max(wmax_i, k >> 5);
+                            if (atomicAdd(&sh->nhit[sp], 1) == 0) { sh->hit_k[sp] = k; sh->hit_j[sp] = j; }
                         }
                     }
                 }
@@ -443,11 +445,29 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                 // the slot used one step ago has been read by everyone (they all passed this barrier);
                 // it is next written two steps from now, after another barrier
                 const int old_slot = (sp + 2) % 3;
-                sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1;
+                sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1; sh->nhit[old_slot] = 0;
                 sh->tr[TR_RELAX]++;
             }
             if (whi >= 0) {
-                if (warp_id() == 0) {
+                if (sh->nhit[sp] == 1) {
+                    // the common case, one hit: its (position, column) was published by the thread that found it, so the
+                    // swap needs no bitmap walk (three dependent shared loads instead of about twelve)
+                    if (tid == 0) {
+                        const int k = sh->hit_k[sp], j = sh->hit_j[sp];
+                        S.bitmap[k >> 5] = 0u;
+                        int fin = -1, nhi = hi;
+                        if (S.y[j] < 0) {
+                            fin = j;
+                        } else {
+                            const int c2 = S.cols[hi];
+                            S.cols[k] = c2; S.pos[c2] = k;
+                            S.cols[hi] = j; S.pos[j] = hi;
+                            nhi = hi + 1;
+                        }
+                        sh->hi = nhi; sh->final_j = fin;
+                        B200LAP_PROF(sh->tr[TR_RELAX_HITS] += 1);
+                    }
+                } else if (warp_id() == 0) {
                     const int wlo = sh->minw[sp];
                     replay_relax(S, hi, wlo, whi);
                 }
@@ -683,6 +703,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     if (tid == 0) {
         sh.s_cnt = 0;
         sh.minw[0] = sh.minw[1] = sh.minw[2] = 0x7fffffff;
+        sh.nhit[0] = sh.nhit[1] = sh.nhit[2] = 0;
         sh.maxw[0] = sh.maxw[1] = sh.maxw[2] = -1;
         for (int q = 0; q < kTraceWords; ++q) sh.tr[q] = 0;
     }
