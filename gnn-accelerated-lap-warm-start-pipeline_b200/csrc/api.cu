@@ -56,6 +56,8 @@ struct b200lap_ctx {
     int max_dyn_smem = 227 * 1024 - 4096;
     int solver_threads = 0;      // option: force the solver block size (tests)
     int force_global_state = 0;  // option: keep solver state in global memory (tests)
+    int solver_cluster = 0;      // option: CTAs per instance (thread-block cluster), 0 = auto, 1 = single CTA
+    int solver_cluster_min_n = 8192;   // option: auto mode uses a cluster from this size on
     int front_rows_per_cta = 0;  // option
     int mlp_impl = 0;            // option: 0 = default
     int feat_ept = 0;            // option: entries per thread of the row-feature kernel (0 = auto)
@@ -230,6 +232,30 @@ int run_front_end(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, 
 }
 
 // ---- solve ----------------------------------------------------------------------------------------
+// launch `batch` thread-block clusters of `cluster` CTAs each (one cluster per instance)
+template <typename K, typename A>
+cudaError_t launch_clustered(K kernel, int batch, int cluster, int T, size_t smem, cudaStream_t stream, const A& args)
+{
+#ifdef B200LAP_EMUL
+    (void)kernel; (void)batch; (void)cluster; (void)T; (void)smem; (void)stream; (void)args;
+    return cudaErrorInvalidValue;
+#else
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)batch * (unsigned)cluster);
+    cfg.blockDim = dim3((unsigned)T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+#endif
+}
+
 template <typename CT>
 int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int batch, int n, const double* u_seed,
               const double* v_seed, double eps, int mode, int* x, int* y, int* rc, long long* trace, double* v_out)
@@ -256,7 +282,17 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
     a.colmin = colmin; a.colarg = colarg;
     const size_t state = solver_state_bytes(n);
     size_t smem = 0;
-    a.smem_mask = solver_place_state(n, ctx->force_global_state ? 0 : (size_t)ctx->max_dyn_smem, &smem);
+    // cluster mode (solver.cuh): relax steps spread over the CTAs of a thread-block cluster, state in the global workspace
+    int cluster = ctx->solver_cluster;
+    if (cluster < 0) cluster = 0;
+    if (cluster == 0) cluster = n >= ctx->solver_cluster_min_n ? 8 : 1;     // auto: measured best at n = 8192 and 16384 (tools/sweep_cluster.py)
+    if (cluster > 8) cluster = 8;
+    if (cluster > 1 && n < 32 * cluster) cluster = 1;
+#ifdef B200LAP_EMUL
+    cluster = 1;
+#endif
+    a.smem_mask = solver_place_state(n, ctx->force_global_state ? 0 : (size_t)ctx->max_dyn_smem, &smem,
+                                     cluster > 1 ? kClusterSmemArrays : (1 << ST_COUNT) - 1);
     a.gws = nullptr; a.gws_stride = 0;
     if (a.smem_mask != (1 << ST_COUNT) - 1) {
         const size_t stride = (state + 4096 + 255) & ~(size_t)255;
@@ -265,6 +301,11 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
         a.gws = g; a.gws_stride = (long long)stride;
     }
     a.x = x; a.y = y; a.rc = rc; a.trace = trace; a.v_out = v_out;
+    a.cluster = cluster; a.boxes = nullptr;
+    if (cluster > 1) {
+        TAKE(boxes, ClusterBox, (size_t)batch);
+        a.boxes = boxes;
+    }
     int T = ctx->solver_threads > 0 ? ctx->solver_threads : round_up((n + 3) / 4, 32);
     if (T > 1024) T = 1024;
     if (T < 32) T = 32;
@@ -273,7 +314,8 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
     do {                                                                                                                   \
         auto k = T <= 512 ? k_solve<CT, MAXC_, 512> : k_solve<CT, MAXC_, 1024>;                                            \
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024))); \
-        B200LAP_LAUNCH(k, dim3(batch), dim3(T), smem, ctx->stream, a);                                                     \
+        if (cluster > 1) CK(launch_clustered(k, batch, cluster, T, smem, ctx->stream, a));                                \
+        else B200LAP_LAUNCH(k, dim3(batch), dim3(T), smem, ctx->stream, a);                                                \
     } while (0)
     if (per_thread <= 4) SOLVE(4);
     else if (per_thread <= 8) SOLVE(8);
@@ -383,6 +425,8 @@ int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value) {
     const std::string k(key);
     if (k == "solver_threads") ctx->solver_threads = (int)value;
     else if (k == "force_global_state") ctx->force_global_state = (int)value;
+    else if (k == "solver_cluster") ctx->solver_cluster = (int)value;
+    else if (k == "solver_cluster_min_n") ctx->solver_cluster_min_n = (int)value;
     else if (k == "solver_smem_budget") ctx->max_dyn_smem = value > 0 ? (int)value : 227 * 1024 - 4096;
     else if (k == "front_rows_per_cta") ctx->front_rows_per_cta = (int)value;
     else if (k == "mlp_impl") ctx->mlp_impl = (int)value;

@@ -49,6 +49,7 @@ struct SolverShared {
     long long tr[kTraceWords];
 };
 
+struct ClusterBox;
 template <typename CT> struct SolveArgs {
     const CT* C;
     long long inst_stride;
@@ -71,6 +72,8 @@ template <typename CT> struct SolveArgs {
     int* rc;                // [B] out
     long long* trace;       // [B][kTraceWords] out (nullable)
     double* v_out;          // [B][n] final column potentials (nullable)
+    int cluster;            // CTAs per instance (thread-block cluster size), 1 = single CTA
+    ClusterBox* boxes;      // [B] mailboxes (cluster mode)
 };
 
 // State arrays in placement priority order (hottest first): a relax step reads d, pos, v of every
@@ -85,13 +88,16 @@ __host__ __device__ inline size_t state_array_bytes(int a, int n) {
     return n8 * 4;
 }
 // greedy placement under a shared-memory budget -> (mask, shared bytes)
-__host__ inline int solver_place_state(int n, size_t budget, size_t* smem_bytes) {
+// `allowed`: arrays that may live in shared memory at all.  In cluster mode only the arrays the master alone
+// touches (y, cols, x, free_rows) qualify; d, pos, v, pred and the bitmap are shared with the worker CTAs.
+constexpr int kClusterSmemArrays = (1 << ST_Y) | (1 << ST_COLS) | (1 << ST_X) | (1 << ST_FREE);
+__host__ inline int solver_place_state(int n, size_t budget, size_t* smem_bytes, int allowed = (1 << ST_COUNT) - 1) {
     int mask = 0;
     size_t used = 0;
     const int order[ST_COUNT] = {ST_BITMAP, ST_D, ST_POS, ST_V, ST_Y, ST_COLS, ST_PRED, ST_X, ST_FREE};
     for (int q = 0; q < ST_COUNT; ++q) {
         const size_t b = state_array_bytes(order[q], n);
-        if (used + b <= budget) { used += b; mask |= 1 << order[q]; }
+        if ((allowed >> order[q] & 1) && used + b <= budget) { used += b; mask |= 1 << order[q]; }
     }
     *smem_bytes = used;
     return mask;
@@ -100,6 +106,22 @@ __host__ inline int solver_place_state(int n, size_t budget, size_t* smem_bytes)
 __host__ __device__ inline size_t solver_state_bytes(int n) {
     const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
     return n8 * 8 * 2 + n8 * 4 * 6 + (((size_t)n + 31) / 32 + 4) * 4;
+}
+
+// ---- cluster mode (large instances): the relax step of the Dijkstra search is spread over the CTAs of a
+// thread-block cluster.  CTA 0 (the master) runs the solver as usual on state kept in the L2-resident global
+// workspace; at each relax step it posts (row, level, slack, hi, slot) in a mailbox, the cluster barrier
+// releases the workers, every CTA relaxes its own slice of columns, a second cluster barrier publishes the
+// d/pred updates and the hit flags, and the master replays the hits.  Workers sit in worker_loop.
+enum { BOX_RELAX = 1, BOX_EXIT = 2 };
+struct ClusterBox {
+    int op, row, js, hi, sp;
+    int minw[3], maxw[3], nhit[3], hit_k[3], hit_j[3];
+};
+__device__ __forceinline__ void cluster_sync_all() {
+#ifndef B200LAP_EMUL
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
 }
 
 template <typename CT> struct SolverCtx {
@@ -111,6 +133,9 @@ template <typename CT> struct SolverCtx {
     SolverShared* sh;
     Red R;
     int step;   // relax/collect step counter (selects the minw/maxw slot)
+    int *minw, *maxw, *nhit, *hit_k, *hit_j;   // slot arrays: in SolverShared, or in the cluster mailbox (cluster mode)
+    int nc, rank;                              // thread-block cluster size and this CTA's rank (1, 0 without a cluster)
+    struct ClusterBox* box;                    // cluster mailbox in global memory (null without a cluster)
 };
 
 // Cycle-level phase counters (trace words 11..19) are compiled in only with -DB200LAP_SOLVER_PROFILE
@@ -287,6 +312,70 @@ __device__ __forceinline__ void replay_relax(SolverCtx<CT>& S, int hi_in, int wl
     }
 }
 
+// ---- cluster mode: one CTA's slice of a relax step (same arithmetic and flags as the single-CTA body) ----------
+template <typename CT>
+__device__ __forceinline__ void relax_slice(SolverCtx<CT>& S, int i, int js, int hi, int sp)
+{
+    const int n = S.n, T = blockDim.x, tid = threadIdx.x;
+    const int per = (n + S.nc - 1) / S.nc;
+    const int j0 = S.rank * per, j1 = min(n, j0 + per);
+    const CT* crow = S.C + (size_t)i * S.ld;
+    // level and slack of the scanned column are fetched by every thread itself (one broadcast address each, in
+    // flight together with the slice): the master posts the step without waiting for them
+    const CT c_js = __ldg(crow + js);
+    const double v_js = S.v[js];
+    const double level = S.d[js];        // js is a SCAN column: no relax step writes its distance
+    const double slack = ((double)c_js - v_js) - level;
+    int wmin_i = 0x7fffffff, wmax_i = -1;
+    for (int base = j0 + tid; base < j1; base += 4 * T) {
+        CT cr[4];
+        int kq[4];
+        double vq[4], dq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = base + q * T;
+            cr[q] = j < j1 ? __ldg(crow + j) : (CT)0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = base + q * T;
+            kq[q] = j < j1 ? S.pos[j] : -1;
+            vq[q] = j < j1 ? S.v[j] : 0.0;
+            dq[q] = j < j1 ? S.d[j] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = base + q * T, k = kq[q];
+            if (k >= hi) {
+                const double cand = ((double)cr[q] - vq[q]) - slack;
+                if (cand < dq[q]) {
+                    S.d[j] = cand;
+                    S.pred[j] = i;
+                    if (cand == level) {
+                        atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
+                        wmin_i = min(wmin_i, k >> 5);
+                        wmax_i = max(wmax_i, k >> 5);
+                        if (atomicAdd(&S.nhit[sp], 1) == 0) { S.hit_k[sp] = k; S.hit_j[sp] = j; }
+                    }
+                }
+            }
+        }
+    }
+    if (wmax_i >= 0) { atomicMin(&S.minw[sp], wmin_i); atomicMax(&S.maxw[sp], wmax_i); }
+}
+
+template <typename CT>
+__device__ void worker_loop(SolverCtx<CT>& S)
+{
+    for (;;) {
+        cluster_sync_all();                                   // a command is posted
+        const int op = S.box->op;
+        if (op == BOX_EXIT) return;
+        relax_slice(S, S.box->row, S.box->js, S.box->hi, S.box->sp);
+        cluster_sync_all();                                   // slices done, flags and d/pred visible
+    }
+}
+
 // ---- one shortest augmenting path (find_path_dense) ---------------------------------------------
 template <int MAXC, bool SMALLREG, typename CT>
 __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
@@ -360,13 +449,13 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
             } else {
                 for (int k = k0; k < k1; ++k) flag_record(k, S.d[S.cols[k]]);
             }
-            if (wmax_i >= 0) { atomicMin(&sh->minw[sp], wmin_i); atomicMax(&sh->maxw[sp], wmax_i); }
+            if (wmax_i >= 0) { atomicMin(&S.minw[sp], wmin_i); atomicMax(&S.maxw[sp], wmax_i); }
             __syncthreads();
             if (warp_id() == 0) {
-                int wlo = sh->minw[sp], whi = sh->maxw[sp];
+                int wlo = S.minw[sp], whi = S.maxw[sp];
                 if (lane_id() == 0) {
                     const int old_slot = (sp + 2) % 3;
-                    sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1; sh->nhit[old_slot] = 0;
+                    S.minw[old_slot] = 0x7fffffff; S.maxw[old_slot] = -1; S.nhit[old_slot] = 0;
                     sh->tr[TR_COLLECT]++;
                 }
                 if (whi < 0) { wlo = lo >> 5; whi = wlo; }
@@ -383,11 +472,12 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
         while (final_j < 0 && lo != hi) {
             const int js = S.cols[lo];
             const int i = S.y[js];
-            const double level = S.d[js];
+            const bool solo = S.nc == 1;             // cluster mode: every CTA fetches these three itself (relax_slice)
+            const double level = solo ? S.d[js] : 0.0;
             ++lo;
             const CT* crow = S.C + (size_t)i * S.ld;
-            const CT c_js = __ldg(crow + js);        // issued together with the row loads below
-            const double v_js = S.v[js];
+            const CT c_js = solo ? __ldg(crow + js) : (CT)0;        // issued together with the row loads below
+            const double v_js = solo ? S.v[js] : 0.0;
             const int sp = S.step % 3;
             int wmin_i = 0x7fffffff, wmax_i = -1;
             auto relax_one = [&](int j, int k, double c, double vj, double dj, double slack) {
@@ -400,12 +490,20 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                             atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
                             wmin_i = min(wmin_i, k >> 5);
                             wmax_i = max(wmax_i, k >> 5);
-                            if (atomicAdd(&sh->nhit[sp], 1) == 0) { sh->hit_k[sp] = k; sh->hit_j[sp] = j; }
+                            if (atomicAdd(&S.nhit[sp], 1) == 0) { S.hit_k[sp] = k; S.hit_j[sp] = j; }
                         }
                     }
                 }
             };
-            if constexpr (MAXC > 0) {
+            if (S.nc > 1) {
+                if (tid == 0) {
+                    ClusterBox* bx = S.box;
+                    bx->op = BOX_RELAX; bx->row = i; bx->js = js; bx->hi = hi; bx->sp = sp;
+                }
+                cluster_sync_all();
+                relax_slice(S, i, js, hi, sp);
+                cluster_sync_all();
+            } else if constexpr (MAXC > 0) {
                 // every load of the step (matrix row AND the thread's pos/v/d entries) is issued before the
                 // first dependent instruction: the compiler cannot hoist shared loads over the stores of the
                 // previous column by itself, and a column-at-a-time body costs ~700 cycles per column
@@ -437,23 +535,24 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                 const double slack = ((double)c_js - v_js) - level;
                 for (int j = tid; j < n; j += T) relax_one(j, S.pos[j], (double)crow[j], S.v[j], S.d[j], slack);
             }
-            if (wmax_i >= 0) { atomicMin(&sh->minw[sp], wmin_i); atomicMax(&sh->maxw[sp], wmax_i); }
-            __syncthreads();
+            if (wmax_i >= 0) { atomicMin(&S.minw[sp], wmin_i); atomicMax(&S.maxw[sp], wmax_i); }
+            if (S.nc == 1) __syncthreads();       // (cluster mode: the closing cluster barrier already did this)
             S.step++;
-            const int whi = sh->maxw[sp];
+            // one round trip for the whole slot (in cluster mode these live in the global mailbox)
+            const int whi = S.maxw[sp], nh = S.nhit[sp], hk = S.hit_k[sp], hj = S.hit_j[sp];
             if (tid == 0) {
                 // the slot used one step ago has been read by everyone (they all passed this barrier);
                 // it is next written two steps from now, after another barrier
                 const int old_slot = (sp + 2) % 3;
-                sh->minw[old_slot] = 0x7fffffff; sh->maxw[old_slot] = -1; sh->nhit[old_slot] = 0;
+                S.minw[old_slot] = 0x7fffffff; S.maxw[old_slot] = -1; S.nhit[old_slot] = 0;
                 sh->tr[TR_RELAX]++;
             }
             if (whi >= 0) {
-                if (sh->nhit[sp] == 1) {
+                if (nh == 1) {
                     // the common case, one hit: its (position, column) was published by the thread that found it, so the
                     // swap needs no bitmap walk (three dependent shared loads instead of about twelve)
                     if (tid == 0) {
-                        const int k = sh->hit_k[sp], j = sh->hit_j[sp];
+                        const int k = hk, j = hj;
                         S.bitmap[k >> 5] = 0u;
                         int fin = -1, nhi = hi;
                         if (S.y[j] < 0) {
@@ -468,7 +567,7 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                         B200LAP_PROF(sh->tr[TR_RELAX_HITS] += 1);
                     }
                 } else if (warp_id() == 0) {
-                    const int wlo = sh->minw[sp];
+                    const int wlo = S.minw[sp];
                     replay_relax(S, hi, wlo, whi);
                 }
                 __syncthreads();
@@ -669,7 +768,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
 {
     B200LAP_DYN_SMEM(dyn);
     __shared__ SolverShared sh;
-    const int b = blockIdx.x, n = a.n, T = blockDim.x, tid = threadIdx.x;
+    const int b = a.cluster > 1 ? (int)(blockIdx.x / (unsigned)a.cluster) : (int)blockIdx.x;
+    const int n = a.n, T = blockDim.x, tid = threadIdx.x;
     SolverCtx<CT> S;
     S.C = a.C + (size_t)b * a.inst_stride;
     S.ld = a.ld;
@@ -700,11 +800,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     S.R.r2 = &sh.red2;
     S.R.par = 0;
     S.step = 0;
+    S.nc = a.cluster > 1 ? a.cluster : 1;
+    S.rank = a.cluster > 1 ? (int)(blockIdx.x % (unsigned)a.cluster) : 0;
+    S.box = a.cluster > 1 ? a.boxes + b : nullptr;
+    if (S.nc > 1) { S.minw = S.box->minw; S.maxw = S.box->maxw; S.nhit = S.box->nhit; S.hit_k = S.box->hit_k; S.hit_j = S.box->hit_j; }
+    else { S.minw = sh.minw; S.maxw = sh.maxw; S.nhit = sh.nhit; S.hit_k = sh.hit_k; S.hit_j = sh.hit_j; }
+    if (S.rank != 0) { worker_loop(S); return; }
     if (tid == 0) {
         sh.s_cnt = 0;
-        sh.minw[0] = sh.minw[1] = sh.minw[2] = 0x7fffffff;
-        sh.nhit[0] = sh.nhit[1] = sh.nhit[2] = 0;
-        sh.maxw[0] = sh.maxw[1] = sh.maxw[2] = -1;
+        for (int q = 0; q < 3; ++q) { S.minw[q] = 0x7fffffff; S.nhit[q] = 0; S.maxw[q] = -1; }
         for (int q = 0; q < kTraceWords; ++q) sh.tr[q] = 0;
     }
     for (int w = tid; w < (n + 31) / 32 + 4; w += T) S.bitmap[w] = 0u;
@@ -824,6 +928,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
             a.y[(size_t)b * n + j] = S.y[j];
             if (a.v_out) a.v_out[(size_t)b * n + j] = S.v[j];
         }
+    }
+    if (S.nc > 1) {
+        if (tid == 0) S.box->op = BOX_EXIT;
+        cluster_sync_all();                 // the workers read the command and leave
     }
     if (tid == 0) {
         a.rc[b] = rc;

@@ -167,6 +167,47 @@ def test_batched_device_solve_mid2048(ctx):
         assert tro["tight_edges"] == tr[b][1] and tro["aug_paths"] == tr[b][7] and tro["took_fallback"] == tr[b][3]
 
 
+@pytest.mark.parametrize("cluster", [2, 4, 8])
+def test_cluster_mode_matches_oracle(ctx, cluster):
+    """Cluster mode of the solver (relax steps spread over a thread-block cluster, state in the global workspace)
+    forced on small instances: assignments and the phase counters must equal the oracle's, seeded and cold."""
+    import torch
+    rng = np.random.default_rng(cluster)
+    cases = [(fam, n) for fam in ("uniform", "sparse", "clustered", "metric") for n in (64, 300, 1000)]
+    cases.append(("ties", 256))
+    try:
+        ctx.set_option("solver_cluster", cluster)
+        for fam, n in cases:
+            C = dense_int(n, 20, seed=cluster).astype(np.float64) if fam == "ties" else gen.make_instance(fam, n, seed=11 + n)
+            for sigma in (None, 0.0, 1e-2):
+                u, v = mintrick_seeds(C, rng) if sigma is None else noisy_oracle_seeds(C, sigma)
+                rco, xo, yo, co, tro = _oracle_seeded(C, u, v)
+                Cd = torch.from_numpy(C.astype(np.float32)).cuda()
+                x, y, rc, tr = ctx.solve_seeded(Cd, torch.from_numpy(u).cuda(), torch.from_numpy(v).cuda(), want_trace=True)
+                ctx.sync()
+                assert int(rc[0]) == rco, (fam, n, sigma)
+                if rco == 0:
+                    assert np.array_equal(x[0].cpu().numpy(), xo) and np.array_equal(y[0].cpu().numpy(), yo), (fam, n, sigma)
+                    t = tr[0].cpu().numpy()
+                    assert (tro["aug_paths"], tro["collect_calls"], tro["relax_cols"], tro["arr_iters"]) == (t[7], t[8], t[9], t[6]), (fam, n, sigma)
+            xc, yc, rcc = ctx.solve_cold(Cd)[:3]
+            ctx.sync()
+            xo, yo = oracle.port_lapjv_internal(C)
+            assert int(rcc[0]) == 0 and np.array_equal(xc[0].cpu().numpy(), xo), (fam, n, "cold")
+        # a batch: one cluster per instance
+        n, B = 512, 6
+        batch = gen.mixed_batch(n, B, first_seed=5)
+        Cs = np.stack([c for _, c in batch])
+        us, vs = zip(*[mintrick_seeds(c, rng) for c in Cs])
+        x, y, rc = ctx.solve_seeded(torch.from_numpy(Cs.astype(np.float32)).cuda(), torch.from_numpy(np.stack(us)).cuda(), torch.from_numpy(np.stack(vs)).cuda())
+        ctx.sync()
+        for b in range(B):
+            rco, xo, yo, co, _ = _oracle_seeded(Cs[b], us[b], vs[b])
+            assert int(rc[b]) == rco and np.array_equal(x[b].cpu().numpy(), xo), batch[b][0]
+    finally:
+        ctx.set_option("solver_cluster", 0)
+
+
 def test_large_instances_by_property(ctx):
     """Sizes the oracle does not finish quickly: permutation validity + strong duality of the final potentials."""
     import torch
