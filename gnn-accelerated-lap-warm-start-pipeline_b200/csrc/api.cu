@@ -285,7 +285,9 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
     // cluster mode (solver.cuh): relax steps spread over the CTAs of a thread-block cluster, state in the global workspace
     int cluster = ctx->solver_cluster;
     if (cluster < 0) cluster = 0;
-    if (cluster == 0) cluster = n >= ctx->solver_cluster_min_n ? 8 : 1;     // auto: measured best at n = 8192 and 16384 (tools/sweep_cluster.py)
+    // auto: 8 CTAs measured best at n = 8192 and 16384 (tools/sweep_cluster.py); a cold solve is all column reduction
+    // and ARR on the master, where the cluster only costs (5.6 -> 6.5 s per 8 x 8192 batch), so it stays on one CTA
+    if (cluster == 0) cluster = (n >= ctx->solver_cluster_min_n && mode == 0) ? 8 : 1;
     if (cluster > 8) cluster = 8;
     if (cluster > 1 && n < 32 * cluster) cluster = 1;
 #ifdef B200LAP_EMUL

@@ -89,12 +89,15 @@ __host__ __device__ inline size_t state_array_bytes(int a, int n) {
 }
 // greedy placement under a shared-memory budget -> (mask, shared bytes)
 // `allowed`: arrays that may live in shared memory at all.  In cluster mode only the arrays the master alone
-// touches (y, cols, x, free_rows) qualify; d, pos, v, pred and the bitmap are shared with the worker CTAs.
-constexpr int kClusterSmemArrays = (1 << ST_Y) | (1 << ST_COLS) | (1 << ST_X) | (1 << ST_FREE);
+// touches (y, cols, x, free_rows) qualify, plus v, of which the workers read a global mirror refreshed at the
+// start of every path (v only changes between paths); d, pos, pred and the bitmap are shared with the workers.
+constexpr int kClusterSmemArrays = (1 << ST_V) | (1 << ST_Y) | (1 << ST_COLS) | (1 << ST_X) | (1 << ST_FREE);
 __host__ inline int solver_place_state(int n, size_t budget, size_t* smem_bytes, int allowed = (1 << ST_COUNT) - 1) {
     int mask = 0;
     size_t used = 0;
-    const int order[ST_COUNT] = {ST_BITMAP, ST_D, ST_POS, ST_V, ST_Y, ST_COLS, ST_PRED, ST_X, ST_FREE};
+    const int order_all[ST_COUNT] = {ST_BITMAP, ST_D, ST_POS, ST_V, ST_Y, ST_COLS, ST_PRED, ST_X, ST_FREE};
+    const int order_cluster[ST_COUNT] = {ST_Y, ST_COLS, ST_V, ST_X, ST_FREE, ST_BITMAP, ST_D, ST_POS, ST_PRED};
+    const int* order = allowed == (1 << ST_COUNT) - 1 ? order_all : order_cluster;
     for (int q = 0; q < ST_COUNT; ++q) {
         const size_t b = state_array_bytes(order[q], n);
         if ((allowed >> order[q] & 1) && used + b <= budget) { used += b; mask |= 1 << order[q]; }
@@ -128,6 +131,7 @@ template <typename CT> struct SolverCtx {
     const CT* C;
     int ld, n;
     double *v, *d;
+    double* vg;   // what the worker CTAs read: v itself, or its global mirror when v lives in the master's shared memory
     int *pred, *cols, *pos, *y, *x, *free_rows;
     unsigned int* bitmap;
     SolverShared* sh;
@@ -323,7 +327,7 @@ __device__ __forceinline__ void relax_slice(SolverCtx<CT>& S, int i, int js, int
     // level and slack of the scanned column are fetched by every thread itself (one broadcast address each, in
     // flight together with the slice): the master posts the step without waiting for them
     const CT c_js = __ldg(crow + js);
-    const double v_js = S.v[js];
+    const double v_js = S.vg[js];
     const double level = S.d[js];        // js is a SCAN column: no relax step writes its distance
     const double slack = ((double)c_js - v_js) - level;
     int wmin_i = 0x7fffffff, wmax_i = -1;
@@ -340,7 +344,7 @@ __device__ __forceinline__ void relax_slice(SolverCtx<CT>& S, int i, int js, int
         for (int q = 0; q < 4; ++q) {
             const int j = base + q * T;
             kq[q] = j < j1 ? S.pos[j] : -1;
-            vq[q] = j < j1 ? S.v[j] : 0.0;
+            vq[q] = j < j1 ? S.vg[j] : 0.0;
             dq[q] = j < j1 ? S.d[j] : 0.0;
         }
 #pragma unroll
@@ -388,6 +392,7 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
         S.pos[j] = j;
         S.pred[j] = start_i;
         S.d[j] = c - S.v[j];
+        if (S.vg != S.v) S.vg[j] = S.v[j];     // cluster mode: the workers' copy of v for this path
     });
     __syncthreads();
     int lo = 0, hi = 0, n_ready = 0, final_j = -1;
@@ -794,6 +799,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
         S.pred = (int*)place(ST_PRED);
         S.x = (int*)place(ST_X);
         S.free_rows = (int*)place(ST_FREE);
+        // the workspace stride covers every array, so whatever was placed in shared memory leaves room for the mirror
+        S.vg = (a.cluster > 1 && (a.smem_mask & (1 << ST_V))) ? (double*)gbase : S.v;
     }
     S.sh = &sh;
     S.R.r = &sh.red;
