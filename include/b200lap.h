@@ -59,6 +59,12 @@ int b200lap_ctx_create(int device, void* stream, b200lap_ctx** out);
 void b200lap_ctx_destroy(b200lap_ctx* ctx);
 void* b200lap_ctx_stream(b200lap_ctx* ctx);          /* the cudaStream_t work is enqueued on */
 int b200lap_ctx_sync(b200lap_ctx* ctx);
+/* Tuning / test options (0 = automatic unless stated): solver_threads, solver_cluster (CTAs per instance: 1 = single
+ * CTA, 2/4/8 = thread-block cluster; auto = 8 from solver_cluster_min_n = 8192 on), force_global_state,
+ * solver_smem_budget, front_rows_per_cta, mlp_impl (1 = FFMA instead of tcgen05), feat_impl (1 = register-resident
+ * row-feature kernel), feat_threads, feat_nbuf, feat_nsamp, feat_ctas, feat_ept.  Unknown keys return
+ * B200LAP_ERR_ARG.  No option changes an assignment or a selected order statistic; the feat_* launch shapes change
+ * floating-point summation orders (features stay inside the stated 1e-4 tolerance). */
 int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value);
 long long b200lap_ctx_launch_count(b200lap_ctx* ctx); /* kernels launched so far on this context */
 const char* b200lap_last_error(void);
