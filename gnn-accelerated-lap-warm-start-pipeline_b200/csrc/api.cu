@@ -14,6 +14,7 @@
 #include "solver.cuh"
 #include "features.cuh"
 #include "features_smem.cuh"
+#include "features_warp.cuh"
 #include "mlp.cuh"
 #include "mlp_tc.cuh"
 #include "../../include/b200lap.h"

@@ -74,6 +74,10 @@ struct FeatSmemArgs {
     int delta;             // half width of the sample-rank bracket
     int kcap;              // thread-private list capacity (multiple of 4, or >= entries per thread)
     int use_bulk;          // rows arrive by cp.async.bulk (needs 16-byte aligned rows)
+    const int* rows_in;        // optional indirection: process rows rows_in[0 .. *rows_in_count) (global row ids b*n + row)
+    const int* rows_in_count;
+    int* redo_list;            // warp kernel: rows handed to the CTA kernel's exact fall-backs
+    int* redo_count;
 };
 
 // ---- order-preserving integer image of a binary32 value (for warp redux min / max) -----------------
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_row_features_smem(FeatSmemArgs a
     float* rowbuf = reinterpret_cast<float*>(smem_raw + sizeof(FeatSmemFixed));
     float* list = rowbuf + (size_t)a.nbuf * a.row_floats;
     float* samp = list + (size_t)a.kcap * T;
-    const long long total_rows = (long long)a.batch * n;
+    const long long total_rows = a.rows_in ? (long long)*a.rows_in_count : (long long)a.batch * n;
     int par = 0, hpar = 0;
 
     for (int i = tid; i < 2 * kSelBins; i += T) (&F.hist[0][0])[i] = 0;
@@ -391,7 +395,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_row_features_smem(FeatSmemArgs a
 #endif
     __syncthreads();
 
-    auto row_ptr = [&](long long r) { return a.C + (r / n) * a.inst_stride + (r % n) * (long long)a.ld; };
+    auto actual = [&](long long q) -> long long { return a.rows_in ? (long long)a.rows_in[q] : q; };
+    auto row_ptr = [&](long long q) { const long long r = actual(q); return a.C + (r / n) * a.inst_stride + (r % n) * (long long)a.ld; };
     // start the arrival of row r in buffer `slot` (bulk: thread 0 only, asynchronous; else cooperative + barrier later)
     auto start_row = [&](long long r, int slot) {
         float* dst = rowbuf + (size_t)slot * a.row_floats;
@@ -445,7 +450,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_row_features_smem(FeatSmemArgs a
         __syncthreads();
 #endif
         const float* buf = rowbuf + (size_t)slot * a.row_floats;
-        const int b = (int)(r / n), row = (int)(r % n);
+        const long long ra = actual(r);
+        const int b = (int)(ra / n), row = (int)(ra % n);
         const float* cm = a.colmin + (size_t)b * n;
 
         // every key of the row the thread owns, through a key transform (fall-back paths and rare extra passes)

@@ -252,3 +252,36 @@ def test_row_features_streaming_kernel(emu):
     finally:
         for k in ("feat_threads", "feat_nbuf", "feat_nsamp"):
             _opt(lib, ctx, k, 0)
+
+
+def test_row_features_warp_kernel(emu):
+    """The one-warp-per-row kernel (features_warp.cuh, n = 512) with its redo hand-over to the CTA kernel: uniform,
+    1e6-fill (count-only tie variant), clamped-at-zero rows, ties around the median, sorted / periodic rows."""
+    from oracle import features_np
+    lib, ctx = emu
+    rng = np.random.default_rng(512)
+    n = 512
+    C = rng.uniform(0, 1, (n, n))
+    j = np.arange(n)
+    fill = rng.uniform(size=(128, n)) > 0.3
+    C[16:144][fill] = 1e6                                        # sparse family rows
+    C[144:208] = np.clip(C[144:208] - 0.4 + 0.1 * rng.normal(size=(64, n)), 0, None)   # clustered-style zeros
+    C[0] = 3.25
+    C[1] = np.where(j < n // 2, 0.0, 1.0)
+    C[2] = j
+    C[3] = j[::-1] * 0.5
+    C[4] = j % 4
+    C[5] = 1000.0; C[5, 17] = 0.0
+    C[6] = rng.integers(0, 3, n)
+    C[7] = np.where(j % 2 == 0, 5.0, rng.uniform(4.9, 5.1, n))
+    C[8] = rng.normal(50, 10, n)
+    C[9] = np.exp(rng.normal(0, 4, n))
+    C[10, :40] = 0.0
+    C = C.astype(np.float32).astype(np.float64)
+    ref = features_np.row_features(C)
+    Cf = np.ascontiguousarray(C, dtype=np.float32)
+    feat = np.zeros((n, 21), np.float32)
+    topv = np.zeros((n, 16), np.float32)
+    assert lib.b200lap_dev_row_features(ctx, Cf.ctypes.data, 0, 1, n, 16, None, feat.ctypes.data, topv.ctypes.data) == 0
+    feature_close(feat, ref, rtol=1e-4)
+    assert np.array_equal(topv, np.sort(Cf, axis=1)[:, :16])
