@@ -304,11 +304,7 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
         a.gws = g; a.gws_stride = (long long)stride;
     }
     a.x = x; a.y = y; a.rc = rc; a.trace = trace; a.v_out = v_out;
-    a.cluster = cluster; a.boxes = nullptr;
-    if (cluster > 1) {
-        TAKE(boxes, ClusterBox, (size_t)batch);
-        a.boxes = boxes;
-    }
+    a.cluster = cluster;
     int T = ctx->solver_threads > 0 ? ctx->solver_threads : round_up((n + 3) / 4, 32);
     if (T > 1024) T = 1024;
     if (T < 32) T = 32;
@@ -317,8 +313,13 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
     do {                                                                                                                   \
         auto k = T <= 512 ? k_solve<CT, MAXC_, 512> : k_solve<CT, MAXC_, 1024>;                                            \
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024))); \
-        if (cluster > 1) CK(launch_clustered(k, batch, cluster, T, smem, ctx->stream, a));                                \
-        else B200LAP_LAUNCH(k, dim3(batch), dim3(T), smem, ctx->stream, a);                                                \
+        bool clustered = cluster > 1;                                                                                      \
+        if (clustered && launch_clustered(k, batch, cluster, T, smem, ctx->stream, a) != cudaSuccess) {                    \
+            /* a cluster shape the device refuses: same kernel, one CTA per instance (the state placement stays valid) */  \
+            (void)cudaGetLastError();                                                                                      \
+            a.cluster = 1; clustered = false;                                                                              \
+        }                                                                                                                  \
+        if (!clustered) B200LAP_LAUNCH(k, dim3(batch), dim3(T), smem, ctx->stream, a);                                     \
     } while (0)
     if (per_thread <= 4) SOLVE(4);
     else if (per_thread <= 8) SOLVE(8);

@@ -44,12 +44,12 @@ struct SolverShared {
     int hi, final_j, next_row, aux;
     int minw[3], maxw[3];   // hit-word ranges, rotated over 3 steps (reset one step after use)
     int nhit[3], hit_k[3], hit_j[3];   // relax steps: number of hits and the first one published (same rotation)
+    int box_op, box_row, box_js, box_hi, box_sp;   // cluster mode: the master's command mailbox, read by the workers through DSMEM
     unsigned int cursor, deferred;
     int hitk[64];           // positions of the flagged records of a collect step, ascending
     long long tr[kTraceWords];
 };
 
-struct ClusterBox;
 template <typename CT> struct SolveArgs {
     const CT* C;
     long long inst_stride;
@@ -73,7 +73,6 @@ template <typename CT> struct SolveArgs {
     long long* trace;       // [B][kTraceWords] out (nullable)
     double* v_out;          // [B][n] final column potentials (nullable)
     int cluster;            // CTAs per instance (thread-block cluster size), 1 = single CTA
-    ClusterBox* boxes;      // [B] mailboxes (cluster mode)
 };
 
 // State arrays in placement priority order (hottest first): a relax step reads d, pos, v of every
@@ -113,14 +112,40 @@ __host__ __device__ inline size_t solver_state_bytes(int n) {
 
 // ---- cluster mode (large instances): the relax step of the Dijkstra search is spread over the CTAs of a
 // thread-block cluster.  CTA 0 (the master) runs the solver as usual on state kept in the L2-resident global
-// workspace; at each relax step it posts (row, level, slack, hi, slot) in a mailbox, the cluster barrier
+// workspace; at each relax step it posts (row, scanned column, hi, slot) in a mailbox IN ITS SHARED MEMORY, which the
+// workers read through distributed shared memory (ld.shared::cluster); the cluster barrier
 // releases the workers, every CTA relaxes its own slice of columns, a second cluster barrier publishes the
-// d/pred updates and the hit flags, and the master replays the hits.  Workers sit in worker_loop.
+// d/pred updates and the hit flags (hit slots: atom/st.shared::cluster on the master's shared memory), and the master
+// replays the hits from its own shared memory.  Workers sit in worker_loop.
 enum { BOX_RELAX = 1, BOX_EXIT = 2 };
-struct ClusterBox {
-    int op, row, js, hi, sp;
-    int minw[3], maxw[3], nhit[3], hit_k[3], hit_j[3];
-};
+// distributed-shared-memory accessors (32-bit shared::cluster addresses; a CTA may address its own window this way too)
+#ifndef B200LAP_EMUL
+__device__ __forceinline__ unsigned dsm_map(const void* local_smem, unsigned cta_rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem)), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ int dsm_ld(unsigned addr) {
+    int v;
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dsm_st(unsigned addr, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ int dsm_add(unsigned addr, int v) {
+    int o;
+    asm volatile("atom.shared::cluster.add.s32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory");
+    return o;
+}
+__device__ __forceinline__ void dsm_min(unsigned addr, int v) { int o; asm volatile("atom.shared::cluster.min.s32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void dsm_max(unsigned addr, int v) { int o; asm volatile("atom.shared::cluster.max.s32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(v) : "memory"); }
+#else
+__device__ __forceinline__ unsigned dsm_map(const void*, unsigned) { return 0; }
+__device__ __forceinline__ int dsm_ld(unsigned) { return 0; }
+__device__ __forceinline__ void dsm_st(unsigned, int) {}
+__device__ __forceinline__ int dsm_add(unsigned, int) { return 0; }
+__device__ __forceinline__ void dsm_min(unsigned, int) {}
+__device__ __forceinline__ void dsm_max(unsigned, int) {}
+#endif
 __device__ __forceinline__ void cluster_sync_all() {
 #ifndef B200LAP_EMUL
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -139,7 +164,7 @@ template <typename CT> struct SolverCtx {
     int step;   // relax/collect step counter (selects the minw/maxw slot)
     int *minw, *maxw, *nhit, *hit_k, *hit_j;   // slot arrays: in SolverShared, or in the cluster mailbox (cluster mode)
     int nc, rank;                              // thread-block cluster size and this CTA's rank (1, 0 without a cluster)
-    struct ClusterBox* box;                    // cluster mailbox in global memory (null without a cluster)
+    unsigned msh;                              // cluster mode: shared::cluster address of the MASTER's SolverShared
 };
 
 // Cycle-level phase counters (trace words 11..19) are compiled in only with -DB200LAP_SOLVER_PROFILE
@@ -359,13 +384,19 @@ __device__ __forceinline__ void relax_slice(SolverCtx<CT>& S, int i, int js, int
                         atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
                         wmin_i = min(wmin_i, k >> 5);
                         wmax_i = max(wmax_i, k >> 5);
-                        if (atomicAdd(&S.nhit[sp], 1) == 0) { S.hit_k[sp] = k; S.hit_j[sp] = j; }
+                        if (dsm_add(S.msh + (unsigned)offsetof(SolverShared, nhit) + 4u * sp, 1) == 0) {
+                            dsm_st(S.msh + (unsigned)offsetof(SolverShared, hit_k) + 4u * sp, k);
+                            dsm_st(S.msh + (unsigned)offsetof(SolverShared, hit_j) + 4u * sp, j);
+                        }
                     }
                 }
             }
         }
     }
-    if (wmax_i >= 0) { atomicMin(&S.minw[sp], wmin_i); atomicMax(&S.maxw[sp], wmax_i); }
+    if (wmax_i >= 0) {
+        dsm_min(S.msh + (unsigned)offsetof(SolverShared, minw) + 4u * sp, wmin_i);
+        dsm_max(S.msh + (unsigned)offsetof(SolverShared, maxw) + 4u * sp, wmax_i);
+    }
 }
 
 template <typename CT>
@@ -373,9 +404,11 @@ __device__ void worker_loop(SolverCtx<CT>& S)
 {
     for (;;) {
         cluster_sync_all();                                   // a command is posted
-        const int op = S.box->op;
-        if (op == BOX_EXIT) return;
-        relax_slice(S, S.box->row, S.box->js, S.box->hi, S.box->sp);
+        const int op = dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_op));
+        if (op == BOX_EXIT) { cluster_sync_all(); return; }   // the master's shared memory stays alive until everybody has read the command
+        const int row = dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_row)), js = dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_js));
+        const int hi = dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_hi)), sp = dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_sp));
+        relax_slice(S, row, js, hi, sp);
         cluster_sync_all();                                   // slices done, flags and d/pred visible
     }
 }
@@ -501,10 +534,7 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
                 }
             };
             if (S.nc > 1) {
-                if (tid == 0) {
-                    ClusterBox* bx = S.box;
-                    bx->op = BOX_RELAX; bx->row = i; bx->js = js; bx->hi = hi; bx->sp = sp;
-                }
+                if (tid == 0) { sh->box_op = BOX_RELAX; sh->box_row = i; sh->box_js = js; sh->box_hi = hi; sh->box_sp = sp; }
                 cluster_sync_all();
                 relax_slice(S, i, js, hi, sp);
                 cluster_sync_all();
@@ -809,9 +839,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     S.step = 0;
     S.nc = a.cluster > 1 ? a.cluster : 1;
     S.rank = a.cluster > 1 ? (int)(blockIdx.x % (unsigned)a.cluster) : 0;
-    S.box = a.cluster > 1 ? a.boxes + b : nullptr;
-    if (S.nc > 1) { S.minw = S.box->minw; S.maxw = S.box->maxw; S.nhit = S.box->nhit; S.hit_k = S.box->hit_k; S.hit_j = S.box->hit_j; }
-    else { S.minw = sh.minw; S.maxw = sh.maxw; S.nhit = sh.nhit; S.hit_k = sh.hit_k; S.hit_j = sh.hit_j; }
+    S.msh = S.nc > 1 ? dsm_map(&sh, 0u) : 0u;
+    S.minw = sh.minw; S.maxw = sh.maxw; S.nhit = sh.nhit; S.hit_k = sh.hit_k; S.hit_j = sh.hit_j;
     if (S.rank != 0) { worker_loop(S); return; }
     if (tid == 0) {
         sh.s_cnt = 0;
@@ -937,8 +966,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
         }
     }
     if (S.nc > 1) {
-        if (tid == 0) S.box->op = BOX_EXIT;
-        cluster_sync_all();                 // the workers read the command and leave
+        if (tid == 0) sh.box_op = BOX_EXIT;
+        cluster_sync_all();                 // the workers read the command ...
+        cluster_sync_all();                 // ... and only then may the master's shared memory go away
     }
     if (tid == 0) {
         a.rc[b] = rc;
