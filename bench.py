@@ -12,7 +12,7 @@ data-path collective); the timed region is bracketed by barrier + synchronize, t
   value      device-resident throughput (C already in HBM as binary32), CUDA events on the context stream
   e2e        the same step through the host-buffer C ABI (b200lap_pipeline_batch): pinned host float64 in,
              host int64 assignments out, host<->device copies inside the timed region
-  roofline   dominant dense-pass kernel (k_row_features_smem) at algorithmic bytes = one read of C = 4 n^2 B per
+  roofline   dominant dense-pass kernel (the row-feature sweep: k_row_features_warp at n = 2048, k_row_features_smem above) at algorithmic bytes = one read of C = 4 n^2 B per
              instance, timed live with CUDA events; `traffic` = DRAM bytes of one launch from the committed ncu
              capture (profiles/r01_ncu_row_features_smem.json); per-kernel table in `dense_pass`
   cpu_baseline   the oracle's CPU pipeline (NumPy features, NumPy OneGNN, reference-compiled lapjv_seeded when
@@ -356,7 +356,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(B * n * 4 * 2 + rch.nbytes), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"bound": "hbm", "kernel": "k_row_features_smem (21-D features + top-16, one read of C)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "row-feature sweep: k_row_features_warp + the redo pass of k_row_features_smem (21-D features + top-16, one read of C)", "achieved": achieved,
                          "peak": peak, "peak_source": which, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "algorithmic_bytes_per_launch": bytes_one_read, "traffic": load_traffic("n2048_b64")},
             "dense_pass_n2048_b64": dense,
