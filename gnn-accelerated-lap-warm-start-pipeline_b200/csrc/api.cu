@@ -308,6 +308,9 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
     int T = ctx->solver_threads > 0 ? ctx->solver_threads : round_up((n + 3) / 4, 32);
     if (T > 1024) T = 1024;
     if (T < 32) T = 32;
+    // cluster mode: 512-thread CTAs synchronise faster and the 128-register variants do not spill; measured 1.46 s
+    // against 1.66 s for 4 x 8192 (tools/sweep_cluster_threads.py); above 8192 the master needs all 1024 threads
+    if (cluster > 1 && ctx->solver_threads <= 0 && n <= 8192 && T > 512) T = 512;
     const int per_thread = (n + T - 1) / T;      // row entries a thread keeps in registers per step
 #define SOLVE(MAXC_)                                                                                                       \
     do {                                                                                                                   \
