@@ -23,11 +23,11 @@ for n, B in ((2048, 64), (4096, 16)):
         ctx.set_option("feat_impl", impl)
         u64, v64, _ = ctx.predict_duals(model, Cd)
         ref = None
-        for pf in (0, 0):
-            pass
+        for _rep in (0, 1):
+
             ms, out = timed(lambda: ctx.solve_seeded(Cd, u64, v64, want_trace=True))
             x = out[0]
             if ref is None: ref = x.clone()
             tr = out[3].cpu().numpy()
-            print(f"n={n} B={B} feat_impl={impl} prefetch={pf}: {ms:8.2f} ms same={bool(torch.equal(x, ref))} relax={int(tr[:,9].sum())} max_relax={int(tr[:,9].max())} collects={int(tr[:,8].sum())} paths={int(tr[:,7].sum())}", flush=True)
+            print(f"n={n} B={B} feat_impl={impl}: {ms:8.2f} ms same={bool(torch.equal(x, ref))} relax={int(tr[:,9].sum())} max_relax={int(tr[:,9].max())} collects={int(tr[:,8].sum())} paths={int(tr[:,7].sum())}", flush=True)
     ctx.set_option("feat_impl", 0)
