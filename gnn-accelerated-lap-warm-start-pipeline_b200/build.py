@@ -19,6 +19,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "b200lap", "libb200lap.so")
+OUT_PROF = os.path.join(HERE, "b200lap", "libb200lap_prof.so")   # same sources + cycle counters in the solver trace (tools/ only)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -40,25 +41,28 @@ def sources():
                   glob.glob(os.path.join(CSRC, "*.inc")) + [os.path.join(HERE, "..", "include", "b200lap.h")])
 
 
-def stale() -> bool:
-    if not os.path.exists(OUT):
+def stale(out: str = OUT) -> bool:
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
-        return OUT
-    prof = ["-DB200LAP_SOLVER_PROFILE"] if os.environ.get("B200LAP_PROFILE") == "1" else []   # cycle counters in the solver trace
-    cmd = [nvcc_path()] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, os.path.join(CSRC, "api.cu")]
+def build(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
+    """profile=True builds the measurement variant libb200lap_prof.so (-DB200LAP_SOLVER_PROFILE: SM-cycle counters
+    in the solver trace); the tools load it with B200LAP_PROFILE_LIB=1.  The product library never carries them."""
+    out = OUT_PROF if profile else OUT
+    if not force and not stale(out):
+        return out
+    prof = ["-DB200LAP_SOLVER_PROFILE"] if profile else []
+    cmd = [nvcc_path()] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(CSRC, "api.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, profile="--profile" in sys.argv))

@@ -44,6 +44,9 @@ struct SolverShared {
     int hi, final_j, next_row, aux;
     int minw[3], maxw[3];   // hit-word ranges, rotated over 3 steps (reset one step after use)
     int nhit[3], hit_k[3], hit_j[3];   // relax steps: number of hits and the first one published (same rotation)
+    int hit_y[3];                      // register-resident path: row matched to the published hit column, and its potential
+    double hit_v[3];
+    double level;                      // register-resident path: the level a collect step ended with
     int box_op, box_row, box_js, box_hi, box_sp;   // cluster mode: the master's command mailbox, read by the workers through DSMEM
     unsigned int cursor, deferred;
     int hitk[64];           // positions of the flagged records of a collect step, ascending
@@ -73,6 +76,7 @@ template <typename CT> struct SolveArgs {
     long long* trace;       // [B][kTraceWords] out (nullable)
     double* v_out;          // [B][n] final column potentials (nullable)
     int cluster;            // CTAs per instance (thread-block cluster size), 1 = single CTA
+    int regpath;            // 1: augmentation keeps d/v in registers (solver_path.cuh); needs vector-aligned rows
 };
 
 // State arrays in placement priority order (hottest first): a relax step reads d, pos, v of every
@@ -165,6 +169,7 @@ template <typename CT> struct SolverCtx {
     int *minw, *maxw, *nhit, *hit_k, *hit_j;   // slot arrays: in SolverShared, or in the cluster mailbox (cluster mode)
     int nc, rank;                              // thread-block cluster size and this CTA's rank (1, 0 without a cluster)
     unsigned msh;                              // cluster mode: shared::cluster address of the MASTER's SolverShared
+    int regpath;                               // augmentation with register-resident d/v (solver_path.cuh)
 };
 
 // Cycle-level phase counters (trace words 11..19) are compiled in only with -DB200LAP_SOLVER_PROFILE
@@ -207,7 +212,8 @@ __device__ __forceinline__ void row_scan(const CT* __restrict__ crow, int n, F&&
 // mode 0: level collect (_find_dense): every flagged position is a prefix-minimum record or tie.
 // mode 1: relax (_scan_dense): every flagged position reached the level; the first unmatched
 //         one ends the path search.
-template <typename CT>
+// POSD: S.d holds the distances in POSITION order (register-resident path) instead of column order.
+template <typename CT, bool POSD = false>
 __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo, int whi)
 {
     // executed by warp 0 only
@@ -247,7 +253,7 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
             const int cnt = min(32, total - base);
             int my_k = 0, my_j = 0;
             double my_d = INFINITY;
-            if (lane < cnt) { my_k = S.sh->hitk[base + lane]; my_j = S.cols[my_k]; my_d = S.d[my_j]; }
+            if (lane < cnt) { my_k = S.sh->hitk[base + lane]; my_j = S.cols[my_k]; my_d = S.d[POSD ? my_k : my_j]; }
             for (int h = 0; h < cnt; ++h) {
                 const int k = __shfl_sync(kFull, my_k, h);
                 const int j = __shfl_sync(kFull, my_j, h);
@@ -278,7 +284,7 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
                         word &= word - 1;
                         const int k = (w0 + l) * 32 + bpos;
                         const int j = S.cols[k];
-                        const double dj = S.d[j];
+                        const double dj = S.d[POSD ? k : j];
                         if (dj < level) { hi = lo; level = dj; }
                         const int c2 = S.cols[hi];
                         S.cols[k] = c2; S.pos[c2] = k;
@@ -302,6 +308,7 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
     if (lane == 0) {
         S.sh->hi = hi;
         S.sh->final_j = best >= 0 ? S.cols[best] : -1;
+        S.sh->level = level;
         B200LAP_PROF(S.sh->tr[TR_RECORDS] += total; S.sh->tr[TR_CYC_COLLECT_REPLAY] += sm_clock() - t0);
     }
 }
@@ -412,6 +419,10 @@ __device__ void worker_loop(SolverCtx<CT>& S)
         cluster_sync_all();                                   // slices done, flags and d/pred visible
     }
 }
+
+}  // namespace b200lap
+#include "solver_path.cuh"
+namespace b200lap {
 
 // ---- one shortest augmenting path (find_path_dense) ---------------------------------------------
 template <int MAXC, bool SMALLREG, typename CT>
@@ -624,7 +635,12 @@ __device__ void augment_all(SolverCtx<CT>& S, int n_free)
 {
     for (int f = 0; f < n_free; ++f) {
         const int root = S.free_rows[f];
-        int col = shortest_path<MAXC, SMALLREG>(S, root);
+        int col;
+        if constexpr (MAXC > 0 && MAXC % VecOf<CT>::V == 0) {
+            col = S.regpath ? shortest_path_reg<MAXC>(S, root) : shortest_path<MAXC, SMALLREG>(S, root);
+        } else {
+            col = shortest_path<MAXC, SMALLREG>(S, root);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             S.sh->tr[TR_PATHS]++;
@@ -840,6 +856,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     S.nc = a.cluster > 1 ? a.cluster : 1;
     S.rank = a.cluster > 1 ? (int)(blockIdx.x % (unsigned)a.cluster) : 0;
     S.msh = S.nc > 1 ? dsm_map(&sh, 0u) : 0u;
+    S.regpath = (a.regpath && S.nc == 1) ? 1 : 0;
     S.minw = sh.minw; S.maxw = sh.maxw; S.nhit = sh.nhit; S.hit_k = sh.hit_k; S.hit_j = sh.hit_j;
     if (S.rank != 0) { worker_loop(S); return; }
     if (tid == 0) {

@@ -1,4 +1,8 @@
-"""Per-instance cycle breakdown of the batched seeded solve (needs the profile build: B200LAP_PROFILE=1 python build.py --force)."""
+"""Per-instance SM-cycle breakdown of the batched seeded solve.  Needs the measurement build of the library:
+    python gnn-accelerated-lap-warm-start-pipeline_b200/build.py --profile
+    B200LAP_PROFILE_LIB=1 python tools/batch_breakdown.py [regpath]
+Register-resident path: `row` = cycles from the top of a relax step until the scanned row has arrived, `bar` = cycles
+in the step's barrier (trace words 13, 14); the rest of a step is arithmetic, hit publication and bookkeeping."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "gnn-accelerated-lap-warm-start-pipeline_b200")):
@@ -13,11 +17,16 @@ n, B = 2048, 64
 batch = gen.mixed_batch(n, B, first_seed=42)
 Cd = torch.from_numpy(np.stack([c for _, c in batch]).astype(np.float32)).cuda()
 u64, v64, _ = ctx.predict_duals(model, Cd)
-out = ctx.solve_seeded(Cd, u64, v64, want_trace=True); ctx.sync()
-tr = out[3].cpu().numpy()
-order = np.argsort(-tr[:, 15])
-print("idx family      total_Mcyc relax_steps relax_Mcyc cyc/step collects collect_Mcyc cyc/collect paths  other_Mcyc")
-for i in order[:12]:
-    t = tr[i]
-    other = t[15] - t[11] - t[12] - t[13] - t[14]
-    print(f"{i:3d} {batch[i][0]:10s} {t[15]/1e6:10.1f} {t[9]:11d} {t[11]/1e6:10.1f} {t[11]/max(1,t[9]):8.0f} {t[8]:8d} {t[12]/1e6:12.1f} {t[12]/max(1,t[8]):11.0f} {t[7]:5d} {other/1e6:10.1f}")
+for reg in ([int(sys.argv[1])] if len(sys.argv) > 1 else [1, 0]):
+    ctx.set_option("solver_regpath", reg)
+    out = ctx.solve_seeded(Cd, u64, v64, want_trace=True); ctx.sync()
+    tr = out[3].cpu().numpy()
+    order = np.argsort(-tr[:, 15])
+    print(f"regpath={reg}")
+    print("idx family      total_Mcyc relax_steps relax_Mcyc cyc/step  row/step  bar/step collects collect_Mcyc cyc/collect replay/coll rec/coll paths  other_Mcyc")
+    for i in list(order[:6]) + list(order[20:22]) + list(order[40:42]):
+        t = tr[i]
+        other = t[15] - t[11] - t[12]
+        rs, cs = max(1, t[9]), max(1, t[8])
+        print(f"{i:3d} {batch[i][0]:10s} {t[15]/1e6:10.1f} {t[9]:11d} {t[11]/1e6:10.1f} {t[11]/rs:8.0f} {t[13]/rs:9.0f} {t[14]/rs:9.0f} {t[8]:8d} "
+              f"{t[12]/1e6:12.1f} {t[12]/cs:11.0f} {t[17]/cs:11.0f} {t[16]/cs:8.1f} {t[7]:5d} {other/1e6:10.1f}")
