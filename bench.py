@@ -30,8 +30,15 @@ import sys
 import threading
 import time
 
+# One BLAS/OpenMP thread per process, as the reference's scripts pin them (scripts/gnn_benchmark.py:25-31).  This
+# must happen BEFORE numpy is imported anywhere in the process tree: worker processes are spawned, re-import this
+# module and inherit the environment.
+for _var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    os.environ[_var] = "1"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "gnn-accelerated-lap-warm-start-pipeline_b200")
+PYREF = os.path.join(ROOT, "oracle", "_ref", "pyref")    # the reference's own gnn/ + lap/, built by oracle/Makefile (pyref)
 for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
@@ -62,6 +69,13 @@ def load_peaks():
         return 6650.0, "fallback"
 
 
+def bench_config(world: int) -> dict:
+    """The `config` object of both arms (the driver compares them key by key)."""
+    return {"workload": f"{BATCH} mixed-family n={N_INST} instances per GPU (BASELINE configs[1], mid2048), random-init OneGNN h192/L4/k16",
+            "families": list(FAMILIES), "storage": "binary32 C on the device (exact), binary64 solver arithmetic; binary64 on the host",
+            "l2": "inputs (1.07 GB/step) larger than L2", "parallelism": f"instance-sharded x{world}"}
+
+
 def named_state_dict():
     import torch
     from gnn.one_gnn import OneGNN
@@ -86,70 +100,122 @@ def make_batch(rank: int, batch: int = BATCH, n: int = N_INST, out=None):
 
 
 # ---- CPU pipeline (the reference arm / cpu_baseline) ---------------------------------------------------
-_W = {"sd": None, "use_ref": False, "cache": {}}
+# kind "reference": the reference's OWN Python pipeline, unmodified, from oracle/_ref/pyref (gnn.compute_row_features,
+# torch-CPU gnn.OneGNN, lap.lapjv_seeded = its Cython binding over its C++), glued exactly as
+# scripts/gnn_benchmark.py:226-262,289 does on a CPU device.  kind "port": the oracle's restatement (NumPy features,
+# NumPy OneGNN, C port of the solver) -- only when oracle/_ref/pyref did not travel.
+_W = {"sd": None, "kind": None, "C": None, "model": None, "torch": None}
 
 
-def _cpu_init(sd, use_ref):
-    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
-        os.environ[var] = "1"
-    _W["sd"], _W["use_ref"] = sd, use_ref
+def pyref_available() -> bool:
+    return os.path.isdir(os.path.join(PYREF, "lap")) and os.path.isdir(os.path.join(PYREF, "gnn"))
 
 
-def _cpu_instance(key):
-    if key not in _W["cache"]:
-        from solvers import generators as gen
-        fam, n, seed = key
-        _W["cache"] = {key: gen.make_instance(fam, n, seed=seed)}
-    return _W["cache"][key]
+def _cpu_init(sd, kind, path, shape):
+    _W["sd"], _W["kind"] = sd, kind
+    _W["C"] = np.load(path, mmap_mode="c") if path else None
+    assert _W["C"] is None or tuple(_W["C"].shape) == tuple(shape)
+    if kind == "reference":
+        sys.path.insert(0, PYREF)             # ahead of this repo's own drop-in `gnn` / `lap` packages
+        import torch
+        import gnn as ref_gnn
+        import lap as ref_lap
+        assert os.path.dirname(ref_gnn.__file__).startswith(PYREF) and os.path.dirname(ref_lap.__file__).startswith(PYREF)
+        torch.set_num_threads(1)
+        model = ref_gnn.OneGNN(21, hidden=192, layers=4, dropout=0.1, topk=16)
+        model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+        _W["model"], _W["torch"], _W["feat"], _W["lap"] = model.eval(), torch, ref_gnn.compute_row_features, ref_lap
+    else:
+        import oracle
+        oracle.port_lib()
 
 
-def _cpu_prepare(key):
-    _cpu_instance(key)
-    import oracle
-    oracle.port_lib()
-    return 0
+def _cpu_threads(_):
+    """What the worker's numeric libraries actually run with (must be 1 each)."""
+    from threadpoolctl import threadpool_info
+    info = [(d.get("internal_api"), d.get("num_threads")) for d in threadpool_info()]
+    if _W["torch"] is not None:
+        info.append(("torch", _W["torch"].get_num_threads()))
+    return info
 
 
-def _cpu_worker(key):
-    """The oracle's CPU pipeline on one instance: NumPy features (binary64) -> NumPy OneGNN (binary32) ->
-    min-trick -> lapjv_seeded (the reference's own compiled solver when oracle/_ref is present)."""
-    from oracle import pipeline_np
-    C = _cpu_instance(key)
+def _cpu_worker(k):
+    C = np.ascontiguousarray(_W["C"][k])      # a view of the page-cached input file, float64 [n, n]
+    n = C.shape[0]
     t0 = time.perf_counter()
-    pipeline_np.solve(C, _W["sd"], topk=16, use_ref=_W["use_ref"])
+    if _W["kind"] == "reference":
+        torch = _W["torch"]
+        C = np.asarray(C, dtype=np.float64)                                   # scripts/gnn_benchmark.py:226
+        with torch.inference_mode():
+            row_feat = _W["feat"](C)                                          # :242
+            row_tensor = torch.from_numpy(row_feat).float().unsqueeze(0)      # :243
+            cost_batch = torch.from_numpy(C).float().unsqueeze(0)             # :244
+            mask = torch.ones((1, n), dtype=torch.bool)                       # :246
+            outputs = _W["model"](row_tensor, cost=cost_batch, mask=mask)     # :248
+            u_pred = outputs["u"].squeeze(0)[:n].cpu().numpy()                # :251,261
+        v_pred = np.min(C - u_pred[:, None], axis=0)                          # :262
+        _W["lap"].lapjv_seeded(C, u_pred.astype(np.float64), v_pred.astype(np.float64))   # :289 + solvers/lap_solver.py:81-101
+    else:
+        from oracle import pipeline_np
+        pipeline_np.solve(C, _W["sd"], topk=16, use_ref=False)
     return time.perf_counter() - t0
 
 
-def _scipy_worker(key):
+def _scipy_worker(k):
     from scipy.optimize import linear_sum_assignment
-    C = _cpu_instance(key)
+    C = np.ascontiguousarray(_W["C"][k])
     t0 = time.perf_counter()
     linear_sum_assignment(C)
     return time.perf_counter() - t0
 
 
-def cpu_pipeline_throughput(n: int, procs: int, rounds: int = 1):
-    """One instance per worker process (families cycled), `procs` workers, 1 BLAS thread each -> instances/s."""
-    import multiprocessing as mp
-    import oracle
-    oracle.build()
-    use_ref = oracle.ref_available()
-    sd = named_state_dict()
-    keys = [(FAMILIES[k % len(FAMILIES)], n, 42 + k) for k in range(procs)]
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(procs, initializer=_cpu_init, initargs=(sd, use_ref)) as pool:
-        pool.map(_cpu_prepare, keys, chunksize=1)     # generate the instances, load the solver library (untimed)
-        walls, per = [], []
-        for _ in range(rounds):
-            t0 = time.perf_counter()
-            per += pool.map(_cpu_worker, keys, chunksize=1)
-            walls.append(time.perf_counter() - t0)
-        ts = time.perf_counter()
-        sp = pool.map(_scipy_worker, keys, chunksize=1)
-        swall = time.perf_counter() - ts
-    return {"inst_per_s": procs * rounds / sum(walls), "walls": walls, "mean_latency_s": float(np.mean(per)),
-            "kind": "reference" if use_ref else "port", "scipy_inst_per_s": len(sp) / swall,
-            "scipy_mean_latency_s": float(np.mean(sp))}
+class CpuArm:
+    """`procs` worker processes (spawned: they inherit the 1-thread environment set at the top of this file) over
+    the instances of one float64 [batch, n, n] file, handed out one at a time (dynamic balance)."""
+
+    def __init__(self, Ch: np.ndarray, procs: int):
+        import multiprocessing as mp
+        import tempfile
+        import oracle
+        self.kind = "reference" if pyref_available() else "port"
+        if self.kind == "port":
+            oracle.build()
+        self.procs, self.batch = procs, int(Ch.shape[0])
+        fd, self.path = tempfile.mkstemp(suffix=".npy", prefix="b200lap_bench_", dir="/dev/shm" if _shm_has(Ch.nbytes) else None)
+        os.close(fd)
+        np.save(self.path, Ch)
+        self.pool = mp.get_context("spawn").Pool(procs, initializer=_cpu_init, initargs=(named_state_dict(), self.kind, self.path, Ch.shape))
+        info = self.pool.map(_cpu_threads, range(procs), chunksize=1)
+        self.threads = sorted({t for w in info for t in w})
+        assert all(nt == 1 for _, nt in self.threads), f"worker threads are not pinned to 1: {self.threads}"
+
+    def run(self, fn, count: int):
+        t0 = time.perf_counter()
+        per = self.pool.map(fn, range(count), chunksize=1)
+        return time.perf_counter() - t0, per
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+
+def _shm_has(nbytes: int) -> bool:
+    try:
+        st = os.statvfs("/dev/shm")
+        return st.f_bavail * st.f_frsize > nbytes + (256 << 20)
+    except OSError:
+        return False
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 # ---- clocks --------------------------------------------------------------------------------------------
@@ -338,20 +404,28 @@ def run_b200(args):
         achieved = fk["GBps_one_read_of_C"]
         cpu = None
         if not args.skip_cpu:
-            procs = min(os.cpu_count() or 1, 16)
-            c = cpu_pipeline_throughput(N_INST, procs=procs)
-            cpu = {"value": round(c["inst_per_s"], 3), "unit": "instances/s", "cores": procs, "kind": c["kind"],
-                   "sample": f"{procs} mixed-family n={N_INST} instances, one per worker process, 1 thread each "
-                             f"(mean latency {c['mean_latency_s']:.2f} s)",
-                   "scipy_linear_sum_assignment": {"value": round(c["scipy_inst_per_s"], 3), "unit": "instances/s",
-                                                   "mean_latency_s": round(c["scipy_mean_latency_s"], 3)}}
+            procs = host_cores()
+            sample = min(B, max(procs, 32))
+            arm = CpuArm(Ch[:sample], procs)
+            try:
+                arm.run(_cpu_worker, min(sample, procs))                       # untimed: page in torch / BLAS / the solver
+                wall, per = arm.run(_cpu_worker, sample)
+                swall, sper = arm.run(_scipy_worker, sample)
+            finally:
+                arm.close()
+            cpu = {"value": round(sample / wall, 3), "unit": "instances/s", "cores": procs, "kind": arm.kind,
+                   "sample": f"the first {sample} of the step's {B} mixed-family n={N_INST} instances, handed one at a time to {procs} "
+                             f"worker processes, 1 thread each (mean latency {float(np.mean(per)):.2f} s)",
+                   "pipeline": "reference's own gnn.compute_row_features + torch-CPU OneGNN + lap.lapjv_seeded (oracle/_ref/pyref)"
+                               if arm.kind == "reference" else "oracle restatement (NumPy features/MLP + C port of the solver)",
+                   "worker_threads": [list(t) for t in arm.threads],
+                   "scipy_linear_sum_assignment": {"value": round(sample / swall, 3), "unit": "instances/s",
+                                                   "mean_latency_s": round(float(np.mean(sper)), 3)}}
         line = {
             "metric": METRIC, "value": round(world * B / (ms_step * 1e-3), 2), "unit": "instances/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{B} mixed-family n={N_INST} instances per GPU (BASELINE configs[1], mid2048), random-init OneGNN h192/L4/k16",
-                       "families": list(FAMILIES), "storage": "binary32 C (exact), binary64 solver arithmetic",
-                       "l2": "inputs (1.07 GB/step) larger than L2", "parallelism": f"instance-sharded x{world}"},
+            "config": bench_config(world),
             "e2e": {"value": round(world * B / e2e_s, 2), "unit": "instances/s", "h2d_bytes_per_step": int(Ch.nbytes),
                     "d2h_bytes_per_step": int(B * n * 4 * 2 + rch.nbytes), "steps": e2e_steps},
             "gpu_launches": int(launches),
@@ -371,22 +445,31 @@ def run_b200(args):
 
 # ---- the reference arm -------------------------------------------------------------------------------------
 def run_reference(args):
+    """The reference's own CPU implementation of the path on this box's host cores: every step is the SAME 64
+    instances the B200 arm steps over (rank 0's batch), spread over all host cores, one instance per worker at a time."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    procs = min(os.cpu_count() or 1, 16)
-    c = cpu_pipeline_throughput(N_INST, procs=procs, rounds=args.warmup + args.steps)
-    kind = c["kind"]
-    walls = c["walls"][args.warmup:]
-    v = procs * len(walls) / sum(walls)
+    procs = host_cores()
+    Ch, fams = make_batch(0)
+    arm = CpuArm(Ch, procs)
+    try:
+        for _ in range(args.warmup):
+            arm.run(_cpu_worker, BATCH)
+        walls = [arm.run(_cpu_worker, BATCH)[0] for _ in range(args.steps)]
+    finally:
+        arm.close()
+    v = BATCH * len(walls) / sum(walls)
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "instances/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(1e3 * procs / v, 1), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": round(1e3 * sum(walls) / len(walls), 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{BATCH} mixed-family n={N_INST} instances per GPU (BASELINE configs[1], mid2048), random-init OneGNN h192/L4/k16",
-                       "families": list(FAMILIES)},
-            "cpu_baseline": {"value": round(v, 3), "unit": "instances/s", "cores": procs, "kind": kind,
-                             "sample": f"each step = {procs} mixed-family n={N_INST} instances over {procs} worker processes, 1 thread each"},
+            "config": bench_config(1),
+            "cpu_baseline": {"value": round(v, 3), "unit": "instances/s", "cores": procs, "kind": arm.kind,
+                             "sample": f"each step = the {BATCH} mixed-family n={N_INST} instances of rank 0's batch over {procs} worker processes, 1 thread each",
+                             "pipeline": "reference's own gnn.compute_row_features + torch-CPU OneGNN + lap.lapjv_seeded (oracle/_ref/pyref)"
+                                         if arm.kind == "reference" else "oracle restatement (NumPy features/MLP + C port of the solver)",
+                             "worker_threads": [list(t) for t in arm.threads]},
             "e2e": {"value": round(v, 3), "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -403,7 +486,7 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
-        args.warmup = min(args.warmup, 1)
+        args.warmup = min(args.warmup, 1)      # each step is tens of CPU-seconds: keep the arm inside a few minutes
         args.steps = min(args.steps, 3)
         run_reference(args)
     else:

@@ -26,7 +26,7 @@
 
 namespace b200lap {
 
-constexpr int kTraceWords = 20;
+constexpr int kTraceWords = 40;   // == B200LAP_TRACE_WORDS; words 20.. are fine-grained step timings of the measurement build
 enum TraceSlot {
     TR_PROJ = 0, TR_TIGHT = 1, TR_GREEDY = 2, TR_FALLBACK = 3, TR_MICRO = 4, TR_FREE_CR = 5,
     TR_ARR = 6, TR_PATHS = 7, TR_COLLECT = 8, TR_RELAX = 9, TR_RC = 10,
@@ -35,6 +35,9 @@ enum TraceSlot {
     // records replayed by collect steps, cycles of the serial replays (warp 0), hits replayed by relax steps
     TR_RECORDS = 16, TR_CYC_COLLECT_REPLAY = 17, TR_CYC_RELAX_REPLAY = 18, TR_RELAX_HITS = 19
 };
+
+struct RecTuple { int k, j; double d; };   // one record of a level collect: position, column, distance
+constexpr int kRecCap = 128;
 
 struct SolverShared {
     BlockRed red;
@@ -47,6 +50,7 @@ struct SolverShared {
     int hit_y[3];                      // register-resident path: row matched to the published hit column, and its potential
     double hit_v[3];
     double level;                      // register-resident path: the level a collect step ended with
+    RecTuple rec[kRecCap];             // register-resident path: the records of a collect step, in position order
     int box_op, box_row, box_js, box_hi, box_sp;   // cluster mode: the master's command mailbox, read by the workers through DSMEM
     unsigned int cursor, deferred;
     int hitk[64];           // positions of the flagged records of a collect step, ascending
@@ -212,8 +216,7 @@ __device__ __forceinline__ void row_scan(const CT* __restrict__ crow, int n, F&&
 // mode 0: level collect (_find_dense): every flagged position is a prefix-minimum record or tie.
 // mode 1: relax (_scan_dense): every flagged position reached the level; the first unmatched
 //         one ends the path search.
-// POSD: S.d holds the distances in POSITION order (register-resident path) instead of column order.
-template <typename CT, bool POSD = false>
+template <typename CT>
 __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo, int whi)
 {
     // executed by warp 0 only
@@ -253,7 +256,7 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
             const int cnt = min(32, total - base);
             int my_k = 0, my_j = 0;
             double my_d = INFINITY;
-            if (lane < cnt) { my_k = S.sh->hitk[base + lane]; my_j = S.cols[my_k]; my_d = S.d[POSD ? my_k : my_j]; }
+            if (lane < cnt) { my_k = S.sh->hitk[base + lane]; my_j = S.cols[my_k]; my_d = S.d[my_j]; }
             for (int h = 0; h < cnt; ++h) {
                 const int k = __shfl_sync(kFull, my_k, h);
                 const int j = __shfl_sync(kFull, my_j, h);
@@ -284,7 +287,7 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
                         word &= word - 1;
                         const int k = (w0 + l) * 32 + bpos;
                         const int j = S.cols[k];
-                        const double dj = S.d[POSD ? k : j];
+                        const double dj = S.d[j];
                         if (dj < level) { hi = lo; level = dj; }
                         const int c2 = S.cols[hi];
                         S.cols[k] = c2; S.pos[c2] = k;
@@ -308,7 +311,6 @@ __device__ __forceinline__ void replay_collect(SolverCtx<CT>& S, int lo, int wlo
     if (lane == 0) {
         S.sh->hi = hi;
         S.sh->final_j = best >= 0 ? S.cols[best] : -1;
-        S.sh->level = level;
         B200LAP_PROF(S.sh->tr[TR_RECORDS] += total; S.sh->tr[TR_CYC_COLLECT_REPLAY] += sm_clock() - t0);
     }
 }

@@ -22,6 +22,94 @@
 
 namespace b200lap {
 
+// Measurement build only: step timings of two observer threads (thread 0 = the bookkeeping thread, thread 33 = an
+// ordinary one) in trace words 20 + 10 * observer + stamp.  A stamp is taken when `dep` is available (the predicate
+// makes the clock read wait for it).
+#if defined(B200LAP_SOLVER_PROFILE) && !defined(B200LAP_EMUL)
+#define B200LAP_STAMP(idx, dep)                                                         \
+    do {                                                                                \
+        if (obs >= 0 && (dep)) {                                                        \
+            const long long t_ = clock64();                                             \
+            sh->tr[20 + 10 * obs + (idx)] += t_ - t_last;                               \
+            t_last = t_;                                                                \
+        }                                                                               \
+    } while (0)
+#else
+#define B200LAP_STAMP(idx, dep) do { } while (0)
+#endif
+
+// ---- serial replay of a level collect, d in POSITION order (warp 0) -------------------------------------------
+// The flagged positions (prefix-minimum records and ties, ascending) are turned into (position, column, distance)
+// tuples by the whole warp -- a record's position is not touched by the swaps of earlier records, so column and
+// distance can be fetched up front -- and lane 0 then replays the reference's swaps over the tuples with nothing
+// but one dependent shared-memory load per record on its chain (the next tuple is already in registers).
+template <typename CT>
+__device__ __forceinline__ void replay_collect_pos(SolverCtx<CT>& S, int lo, int wlo, int whi)
+{
+    const int lane = lane_id();
+    const long long t0 = sm_clock();
+    SolverShared* sh = S.sh;
+    int hi = lo, total = 0;
+    double level = INFINITY;
+    for (int w0 = wlo; w0 <= whi; w0 += 32) {
+        unsigned int bits = 0;
+        if (w0 + lane <= whi) { bits = S.bitmap[w0 + lane]; if (bits) S.bitmap[w0 + lane] = 0u; }
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int round_total = __shfl_sync(kFull, incl, 31);
+        for (int c0 = 0; c0 < round_total; c0 += kRecCap) {
+            int idx = incl - cnt - c0;
+            unsigned int w = bits;
+            while (w) {
+                const int bpos = __ffs((int)w) - 1;
+                w &= w - 1;
+                if (idx >= 0 && idx < kRecCap) sh->rec[idx].k = (w0 + lane) * 32 + bpos;
+                ++idx;
+            }
+            __syncwarp();
+            const int m = min(kRecCap, round_total - c0);
+            for (int r = lane; r < m; r += 32) {
+                const int k = sh->rec[r].k;
+                sh->rec[r].j = S.cols[k];
+                sh->rec[r].d = S.d[k];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                RecTuple t = sh->rec[0];
+                for (int r = 0; r < m; ++r) {
+                    const RecTuple nx = sh->rec[r + 1 < m ? r + 1 : r];
+                    if (t.d < level) { hi = lo; level = t.d; }
+                    const int c2 = S.cols[hi];
+                    S.cols[t.k] = c2; S.pos[c2] = t.k;
+                    S.cols[hi] = t.j; S.pos[t.j] = hi;
+                    ++hi;
+                    t = nx;
+                }
+            }
+            __syncwarp();
+        }
+        total += round_total;
+    }
+    hi = __shfl_sync(kFull, hi, 0);
+    if (hi == lo) hi = lo + 1;   // only reachable with NaN distances; keep moving
+    // unmatched column among the collected level: the LAST one in position order wins (lapjv.cpp:250-255)
+    int best = -1;
+    for (int k = lo + lane; k < hi; k += 32)
+        if (S.y[S.cols[k]] < 0) best = k;
+    best = warp_max_i(best);
+    if (lane == 0) {
+        sh->hi = hi;
+        sh->final_j = best >= 0 ? S.cols[best] : -1;
+        sh->level = level;
+        B200LAP_PROF(sh->tr[TR_RECORDS] += total; sh->tr[TR_CYC_COLLECT_REPLAY] += sm_clock() - t0);
+    }
+}
+
 template <typename CT> struct VecOf;
 template <> struct VecOf<float> {
     static constexpr int V = 4;
@@ -107,6 +195,10 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
     bool have_entry = false;
     int pend_j = -1, pend_hi = 0;        // thread 0: the swap of the previous step's single hit, not yet applied
     int n_collect = 0, n_relax = 0;      // thread 0: trace counters, flushed at the end of the path
+#if defined(B200LAP_SOLVER_PROFILE) && !defined(B200LAP_EMUL)
+    const int obs = tid == 0 ? 0 : (tid == 33 ? 1 : -1);
+    long long t_last = 0;
+#endif
     for (;;) {
         if (lo == hi) {
             // ================= level collect (_find_dense) =================
@@ -125,6 +217,8 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
                 }
             }
             __syncthreads();
+            B200LAP_PROF(if (tid == 0) sh->tr[28] += sm_clock() - tc0);
+            const long long tc1 = sm_clock();
             const int L = n - lo;
             const int chunk = (L + T - 1) / T;
             const int k0 = lo + tid * chunk;
@@ -146,6 +240,8 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             const int p = S.R.flip();
             if (lane_id() == 31) S.R.r->d[p][warp_id()] = incl;
             __syncthreads();
+            B200LAP_PROF(if (tid == 0) sh->tr[29] += sm_clock() - tc1);
+            const long long tc2 = sm_clock();
             {
                 const double t = lane_id() < warp_id() ? S.R.r->d[p][lane_id()] : INFINITY;
                 const double wmin = warp_min_d(t);
@@ -166,6 +262,8 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             }
             if (wmax_i >= 0) { atomicMin(&S.minw[sp], wmin_i); atomicMax(&S.maxw[sp], wmax_i); }
             __syncthreads();
+            B200LAP_PROF(if (tid == 0) sh->tr[38] += sm_clock() - tc2);
+            const long long tc3 = sm_clock();
             if (warp_id() == 0) {
                 int wlo = S.minw[sp], whi = S.maxw[sp];
                 if (lane_id() == 0) {
@@ -173,9 +271,10 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
                     S.minw[old_slot] = 0x7fffffff; S.maxw[old_slot] = -1; S.nhit[old_slot] = 0;
                 }
                 if (whi < 0) { wlo = lo >> 5; whi = wlo; }
-                replay_collect<CT, true>(S, lo, wlo, whi);
+                replay_collect_pos(S, lo, wlo, whi);
             }
             __syncthreads();
+            B200LAP_PROF(if (tid == 0) sh->tr[39] += sm_clock() - tc3);
             S.step++;
             ++n_collect;
             hi = sh->hi;
@@ -191,6 +290,9 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
         }
         // ================= one relax step (_scan_dense, one SCAN column) =================
         const long long tr0 = sm_clock();
+#if defined(B200LAP_SOLVER_PROFILE) && !defined(B200LAP_EMUL)
+        t_last = tr0;
+#endif
         if (!have_entry) {
             js = S.cols[lo];
             irow = S.y[js];
@@ -198,6 +300,7 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
         }
         const int sp = S.step % 3;
         const CT* crow = S.C + (size_t)irow * S.ld;
+        B200LAP_STAMP(0, irow >= 0 && vjs == vjs);
         CT cr[MAXC];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -213,9 +316,11 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             S.cols[pend_hi] = pend_j; S.pos[pend_j] = pend_hi;
             pend_j = -1;
         }
+        B200LAP_STAMP(1, pend_j < 0);
         const double slack = ((double)c_js - vjs) - level;
         // profile build: word 13 = cycles until the row arrived (the slack needs c_js), word 14 = cycles in the barrier
         B200LAP_PROF(if (tid == 0 && slack == slack) sh->tr[TR_CYC_ARR_SCAN] += sm_clock() - tr0);
+        B200LAP_STAMP(2, slack == slack);
         unsigned hitm = 0;
 #pragma unroll
         for (int e = 0; e < MAXC; ++e) {
@@ -227,6 +332,14 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
                 if (cand == level) hitm |= 1u << e;
             }
         }
+#if defined(B200LAP_SOLVER_PROFILE) && !defined(B200LAP_EMUL)
+        {
+            double acc_ = 0.0;
+#pragma unroll
+            for (int e = 0; e < MAXC; ++e) acc_ += dq[e];
+            B200LAP_STAMP(3, acc_ == acc_ || hitm);
+        }
+#endif
         if (hitm) {
             todo &= ~hitm;
 #pragma unroll
@@ -242,10 +355,13 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             }
         }
         const long long tb0 = sm_clock();
+        B200LAP_STAMP(4, true);
         __syncthreads();
+        B200LAP_STAMP(5, true);
         B200LAP_PROF(if (tid == 0) sh->tr[TR_CYC_ARR_SERIAL] += sm_clock() - tb0);
         S.step++;
         const int nh = S.nhit[sp];
+        B200LAP_STAMP(6, nh >= 0);
         if (tid == 0) {
             const int old_slot = (sp + 2) % 3;
             S.minw[old_slot] = 0x7fffffff; S.maxw[old_slot] = -1; S.nhit[old_slot] = 0;
@@ -281,6 +397,7 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             final_j = sh->final_j;
             if (final_j >= 0) break;
         }
+        B200LAP_STAMP(7, hi >= 0 && irow >= 0);
         B200LAP_PROF(if (tid == 0) sh->tr[TR_CYC_RELAX] += sm_clock() - tr0);
     }
     // ---- dual update of the READY columns (lapjv.cpp:270-276): level == d[cols[n_ready]]

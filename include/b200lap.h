@@ -21,7 +21,7 @@ extern "C" {
 #define B200LAP_ERR_ARG (-102)
 
 #define B200LAP_ROW_FEAT_DIM 21   /* gnn/features.py:223-241 */
-#define B200LAP_TRACE_WORDS 20
+#define B200LAP_TRACE_WORDS 40
 #define B200LAP_TOPK_MAX 32
 
 typedef struct b200lap_ctx b200lap_ctx;       /* one per (device, stream): workspaces + stream */
@@ -97,7 +97,7 @@ int b200lap_dev_predict_duals(b200lap_ctx* ctx, const b200lap_model* model, cons
 
 /* ------------------------------------------------------------------------------------------
  * 4. Solver half on DEVICE buffers (same matrix conventions).  x,y int32 [batch][n] (written
- *    for instances with rc == 0), rc int32 [batch], trace int64 [batch][20] nullable,
+ *    for instances with rc == 0), rc int32 [batch], trace int64 [batch][B200LAP_TRACE_WORDS] nullable,
  *    v_out binary64 [batch][n] nullable (final column potentials).
  * ------------------------------------------------------------------------------------------ */
 int b200lap_dev_solve_seeded(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const double* u_seed,

@@ -30,3 +30,12 @@ for reg in ([int(sys.argv[1])] if len(sys.argv) > 1 else [1, 0]):
         rs, cs = max(1, t[9]), max(1, t[8])
         print(f"{i:3d} {batch[i][0]:10s} {t[15]/1e6:10.1f} {t[9]:11d} {t[11]/1e6:10.1f} {t[11]/rs:8.0f} {t[13]/rs:9.0f} {t[14]/rs:9.0f} {t[8]:8d} "
               f"{t[12]/1e6:12.1f} {t[12]/cs:11.0f} {t[17]/cs:11.0f} {t[16]/cs:8.1f} {t[7]:5d} {other/1e6:10.1f}")
+    if reg == 1:
+        i = order[0]
+        t = tr[i]
+        rs = max(1, t[9])
+        names = ["addr(LDS chain)", "issue+swap", "row arrives(slack)", "compute 4 cols", "hit publish", "barrier", "nh read", "post"]
+        cs = max(1, t[8])
+        print(f"  collect (thread 0): transpose+bar={t[28]/cs:.0f} scan+bar={t[29]/cs:.0f} flags+bar={t[38]/cs:.0f} replay+bar={t[39]/cs:.0f}")
+        for o, who in ((0, "thread 0"), (1, "thread 33")):
+            print(f"  {who}: " + "  ".join(f"{names[k]}={t[20 + 10 * o + k] / rs:.0f}" for k in range(8)))
