@@ -23,7 +23,7 @@ vp = ctypes.c_void_p
 
 ERR_CUDA, ERR_UNSUPPORTED, ERR_ARG = -100, -101, -102
 ROW_FEAT_DIM = 21
-TRACE_WORDS = 40
+TRACE_WORDS = 48
 TRACE_NAMES = ("proj_triggers", "tight_edges", "greedy_matched", "took_fallback", "micro_bumps", "free_after_cr",
                "arr_iters", "aug_paths", "collect_calls", "relax_cols", "rc", "cyc_relax", "cyc_collect", "cyc_arr_scan",
                "cyc_arr_serial", "cyc_total", "collect_records", "cyc_collect_replay", "cyc_relax_replay", "relax_hits")

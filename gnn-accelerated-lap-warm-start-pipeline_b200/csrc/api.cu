@@ -3,6 +3,7 @@
 // Every entry point enqueues hand-written sm_100a kernels on the context's stream; nothing here
 // computes on the host.  Built by nvcc only (build.py); the same translation unit also compiles
 // against tests/emul/cuda_emul.h for the CPU-side logic tests (test infrastructure, not shipped).
+#include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
@@ -12,6 +13,7 @@
 #include "colsweep.cuh"
 #include "frontend.cuh"
 #include "solver.cuh"
+#include "dualsweep.cuh"
 #include "features.cuh"
 #include "features_smem.cuh"
 #include "features_warp.cuh"
@@ -517,6 +519,119 @@ int b200lap_dev_front_end(b200lap_ctx* ctx, const void* C, int is_f64, int batch
     return is_f64 ? run_front_end(ctx, (const double*)C, st, n, batch, n, u_seed, v_seed, eps, u_tight, tl, tight_cnt, (FrontFlags*)flags)
                   : run_front_end(ctx, (const float*)C, st, n, batch, n, u_seed, v_seed, eps, u_tight, tl, tight_cnt, (FrontFlags*)flags);
 }
+
+}  // extern "C"
+
+// ---- dual-potential sweeps (solvers/advanced_dual.py:14-63) ---------------------------------------------
+namespace {
+
+template <typename CT>
+int run_col_min_reduced(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int batch, int n, const double* u, double* v_cap)
+{
+    const int rps = strip_rows(n);
+    const int S = (n + rps - 1) / rps;
+    TAKE(pval, double, (size_t)batch * S * n);
+    if (vec_ok(C, inst_stride, ld, n)) {
+        constexpr int V = natural_vec<CT>();
+        dim3 grid((n + kColThreads * V - 1) / (kColThreads * V), S, batch);
+        auto k = k_col_min_reduced_partial<CT, V>;
+        B200LAP_LAUNCH(k, grid, dim3(kColThreads), 0, ctx->stream, C, inst_stride, ld, n, rps, u, pval);
+    } else {
+        dim3 grid((n + kColThreads - 1) / kColThreads, S, batch);
+        auto k = k_col_min_reduced_partial<CT, 1>;
+        B200LAP_LAUNCH(k, grid, dim3(kColThreads), 0, ctx->stream, C, inst_stride, ld, n, rps, u, pval);
+    }
+    B200LAP_LAUNCH(k_min_trick_final, dim3((n + 255) / 256, batch), dim3(256), 0, ctx->stream, (const double*)pval, S, n, v_cap);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// min_ij ((c - u_i) - v_j) per instance -> host doubles; optionally writes the reduced-cost matrices
+template <typename CT>
+int run_reduced_costs(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int batch, int n, const double* u, const double* v,
+                      double* out, double* min_host)
+{
+    TAKE(mo, unsigned long long, (size_t)batch);
+    CK(cudaMemsetAsync(mo, 0xff, sizeof(unsigned long long) * (size_t)batch, ctx->stream));
+    int gx = n < ctx->sm_count * 4 ? n : ctx->sm_count * 4;
+    if (out) { auto k = k_reduced_costs<CT, true>; B200LAP_LAUNCH(k, dim3(gx, batch), dim3(256), 0, ctx->stream, C, inst_stride, ld, n, u, v, out, mo); }
+    else { auto k = k_reduced_costs<CT, false>; B200LAP_LAUNCH(k, dim3(gx, batch), dim3(256), 0, ctx->stream, C, inst_stride, ld, n, u, v, out, mo); }
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    std::vector<unsigned long long> h((size_t)batch);
+    CK(cudaMemcpyAsync(h.data(), mo, sizeof(unsigned long long) * (size_t)batch, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < batch; ++b) {
+        const unsigned long long k = h[(size_t)b];
+        const long long bits = (long long)(k ^ (((long long)k < 0) ? 0x8000000000000000ull : 0xffffffffffffffffull));
+        double d;
+        static_assert(sizeof(d) == sizeof(bits), "binary64");
+        memcpy(&d, &bits, sizeof(d));
+        min_host[b] = k == ~0ull ? INFINITY : d;
+    }
+    return 0;
+}
+
+// project_feasible on device buffers of ONE instance (u, v updated in place) -> rounds used
+template <typename CT>
+int run_project_feasible(b200lap_ctx* ctx, const CT* C, int n, double* u, double* v, int max_rounds, double tol, int* rounds_out)
+{
+    const long long st = (long long)n * n;
+    TAKE(cap, double, (size_t)n);
+    TAKE(tl, int, (size_t)n * kTightCap);
+    TAKE(tc, int, (size_t)n);
+    TAKE(flags, FrontFlags, 1);
+    const int rounds = max_rounds < 1 ? 1 : max_rounds;
+    int used = 0;
+    // u_cap_i = min_j (c_ij - v_j) is the front-end sweep's row tightening; the same sweep evaluates the reference's
+    // stopping rule any((c - u_i) - v_j < -tol) for the potentials it is handed
+    int r = run_front_end(ctx, C, st, n, 1, n, u, v, tol, cap, tl, tc, flags);
+    if (r) return r;
+    for (int round = 0; round < rounds; ++round) {
+        ++used;
+        B200LAP_LAUNCH(k_clamp_min, dim3((n + 255) / 256), dim3(256), 0, ctx->stream, u, (const double*)cap, (long long)n);
+        r = run_col_min_reduced(ctx, C, st, n, 1, n, u, cap);
+        if (r) return r;
+        B200LAP_LAUNCH(k_clamp_min, dim3((n + 255) / 256), dim3(256), 0, ctx->stream, v, (const double*)cap, (long long)n);
+        ctx->launches += 2;
+        r = run_front_end(ctx, C, st, n, 1, n, u, v, tol, cap, tl, tc, flags);     // feasibility of (u, v) + next round's u_cap
+        if (r) return r;
+        FrontFlags hf;
+        CK(cudaMemcpyAsync(&hf, flags, sizeof(FrontFlags), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!hf.infeasible) break;
+    }
+    if (rounds_out) *rounds_out = used;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200lap_dev_project_feasible(b200lap_ctx* ctx, const void* C, int is_f64, int n, double* u, double* v, int max_rounds,
+                                 double tol, int* rounds) {
+    if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
+    if (n <= 0) return fail(B200LAP_ERR_ARG, "empty problem");
+    ctx->ws_reset();
+    return is_f64 ? run_project_feasible(ctx, (const double*)C, n, u, v, max_rounds, tol, rounds)
+                  : run_project_feasible(ctx, (const float*)C, n, u, v, max_rounds, tol, rounds);
+}
+
+int b200lap_dev_reduced_costs(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const double* u, const double* v,
+                              double* out, double* min_host) {
+    if (!ctx || !min_host) return fail(B200LAP_ERR_ARG, "null argument");
+    if (n <= 0 || batch <= 0) return fail(B200LAP_ERR_ARG, "empty problem");
+    ctx->ws_reset();
+    const long long st = (long long)n * n;
+    return is_f64 ? run_reduced_costs(ctx, (const double*)C, st, n, batch, n, u, v, out, min_host)
+                  : run_reduced_costs(ctx, (const float*)C, st, n, batch, n, u, v, out, min_host);
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- host-buffer entry points -------------------------------------------------------------------
 namespace {

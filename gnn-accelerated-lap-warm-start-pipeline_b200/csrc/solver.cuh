@@ -26,7 +26,7 @@
 
 namespace b200lap {
 
-constexpr int kTraceWords = 40;   // == B200LAP_TRACE_WORDS; words 20.. are fine-grained step timings of the measurement build
+constexpr int kTraceWords = 48;   // == B200LAP_TRACE_WORDS; words 20.. are fine-grained step timings of the measurement build
 enum TraceSlot {
     TR_PROJ = 0, TR_TIGHT = 1, TR_GREEDY = 2, TR_FALLBACK = 3, TR_MICRO = 4, TR_FREE_CR = 5,
     TR_ARR = 6, TR_PATHS = 7, TR_COLLECT = 8, TR_RELAX = 9, TR_RC = 10,
@@ -38,6 +38,8 @@ enum TraceSlot {
 
 struct RecTuple { int k, j; double d; };   // one record of a level collect: position, column, distance
 constexpr int kRecCap = 128;
+struct HitEntry { int sj, yj; double v; }; // one hit of a batched relax step: (scan index << 24 | column), its row, its potential
+constexpr int kHitCap = 32;
 
 struct SolverShared {
     BlockRed red;
@@ -51,6 +53,8 @@ struct SolverShared {
     double hit_v[3];
     double level;                      // register-resident path: the level a collect step ended with
     RecTuple rec[kRecCap];             // register-resident path: the records of a collect step, in position order
+    HitEntry hl[3][kHitCap];           // register-resident path: hits of a batched relax step (same 3-slot rotation as nhit)
+    int done_scans;                    // register-resident path: scans of the batch the reference would have performed
     int box_op, box_row, box_js, box_hi, box_sp;   // cluster mode: the master's command mailbox, read by the workers through DSMEM
     unsigned int cursor, deferred;
     int hitk[64];           // positions of the flagged records of a collect step, ascending
@@ -87,7 +91,7 @@ template <typename CT> struct SolveArgs {
 // column; the replay and the path flip touch y, cols, pred, x sparsely.  Whatever fits goes to shared
 // memory, the rest to the (L2-resident) global workspace -- n = 8192 keeps d, pos, v, y on chip,
 // n = 16384 keeps d and pos.
-enum StateArray { ST_D = 0, ST_POS, ST_V, ST_Y, ST_COLS, ST_PRED, ST_X, ST_FREE, ST_BITMAP, ST_COUNT };
+enum StateArray { ST_D = 0, ST_POS, ST_V, ST_Y, ST_COLS, ST_PRED, ST_X, ST_FREE, ST_BITMAP, ST_SROW, ST_COUNT };
 __host__ __device__ inline size_t state_array_bytes(int a, int n) {
     const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
     if (a == ST_D || a == ST_V) return n8 * 8;
@@ -102,8 +106,8 @@ constexpr int kClusterSmemArrays = (1 << ST_V) | (1 << ST_Y) | (1 << ST_COLS) | 
 __host__ inline int solver_place_state(int n, size_t budget, size_t* smem_bytes, int allowed = (1 << ST_COUNT) - 1) {
     int mask = 0;
     size_t used = 0;
-    const int order_all[ST_COUNT] = {ST_BITMAP, ST_D, ST_POS, ST_V, ST_Y, ST_COLS, ST_PRED, ST_X, ST_FREE};
-    const int order_cluster[ST_COUNT] = {ST_Y, ST_COLS, ST_V, ST_X, ST_FREE, ST_BITMAP, ST_D, ST_POS, ST_PRED};
+    const int order_all[ST_COUNT] = {ST_BITMAP, ST_D, ST_POS, ST_V, ST_Y, ST_COLS, ST_PRED, ST_X, ST_FREE, ST_SROW};
+    const int order_cluster[ST_COUNT] = {ST_Y, ST_COLS, ST_V, ST_X, ST_FREE, ST_BITMAP, ST_D, ST_POS, ST_PRED, ST_SROW};
     const int* order = allowed == (1 << ST_COUNT) - 1 ? order_all : order_cluster;
     for (int q = 0; q < ST_COUNT; ++q) {
         const size_t b = state_array_bytes(order[q], n);
@@ -115,7 +119,7 @@ __host__ inline int solver_place_state(int n, size_t budget, size_t* smem_bytes,
 
 __host__ __device__ inline size_t solver_state_bytes(int n) {
     const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
-    return n8 * 8 * 2 + n8 * 4 * 6 + (((size_t)n + 31) / 32 + 4) * 4;
+    return n8 * 8 * 2 + n8 * 4 * 7 + (((size_t)n + 31) / 32 + 4) * 4 + 16;
 }
 
 // ---- cluster mode (large instances): the relax step of the Dijkstra search is spread over the CTAs of a
@@ -166,6 +170,7 @@ template <typename CT> struct SolverCtx {
     double *v, *d;
     double* vg;   // what the worker CTAs read: v itself, or its global mirror when v lives in the master's shared memory
     int *pred, *cols, *pos, *y, *x, *free_rows;
+    int* srow;    // register-resident path: row matched to the column at each SCAN-queue position
     unsigned int* bitmap;
     SolverShared* sh;
     Red R;
@@ -805,14 +810,15 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
     return deferred;
 }
 
-template <int MAXC, bool SMALLREG, typename CT>
-__device__ void cold_solve(SolverCtx<CT>& S, const CT* colmin, const int* colarg)
+// returns the number of rows still free (S.free_rows[0..left)): the caller augments them
+template <int MAXC, typename CT>
+__device__ int cold_solve(SolverCtx<CT>& S, const CT* colmin, const int* colarg)
 {
     int left = col_reduce<MAXC>(S, colmin, colarg);
     if (threadIdx.x == 0) S.sh->tr[TR_FREE_CR] = left;
     for (int pass = 0; left > 0 && pass < 2; ++pass) left = arr_pass<MAXC>(S, left);
     __syncthreads();
-    if (left > 0) augment_all<MAXC, SMALLREG>(S, left);
+    return left;
 }
 
 // ---- the persistent per-instance kernel -----------------------------------------------------------
@@ -847,6 +853,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
         S.pred = (int*)place(ST_PRED);
         S.x = (int*)place(ST_X);
         S.free_rows = (int*)place(ST_FREE);
+        S.srow = (int*)place(ST_SROW);
         // the workspace stride covers every array, so whatever was placed in shared memory leaves room for the mirror
         S.vg = (a.cluster > 1 && (a.smem_mask & (1 << ST_V))) ? (double*)gbase : S.v;
     }
@@ -858,7 +865,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     S.nc = a.cluster > 1 ? a.cluster : 1;
     S.rank = a.cluster > 1 ? (int)(blockIdx.x % (unsigned)a.cluster) : 0;
     S.msh = S.nc > 1 ? dsm_map(&sh, 0u) : 0u;
-    S.regpath = (a.regpath && S.nc == 1) ? 1 : 0;
+    S.regpath = (a.regpath && S.nc == 1 && a.smem_mask == (1 << ST_COUNT) - 1) ? 1 : 0;
     S.minw = sh.minw; S.maxw = sh.maxw; S.nhit = sh.nhit; S.hit_k = sh.hit_k; S.hit_j = sh.hit_j;
     if (S.rank != 0) { worker_loop(S); return; }
     if (tid == 0) {
@@ -873,8 +880,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     const long long t_start = sm_clock();
     __syncthreads();
 
+    int n_aug = 0;          // rows left for the augmentation phase (one call site for all three ways to get here)
     if (a.mode == 1) {
-        cold_solve<MAXC, (MAXT > 512)>(S, colmin, colarg);
+        n_aug = cold_solve<MAXC>(S, colmin, colarg);
     } else {
         const double eps = a.eps;
         const double tol = eps > 1e-9 ? eps : 1e-9;
@@ -955,7 +963,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
             if ((double)(long long)tight < 1.2 * n) {
                 if (tid == 0) sh.tr[TR_FALLBACK] = 1;
                 __syncthreads();
-                cold_solve<MAXC, (MAXT > 512)>(S, colmin, colarg);
+                n_aug = cold_solve<MAXC>(S, colmin, colarg);
             } else if (n_free > 0) {
                 // ---- micro-ARR (lapjv_seeded.cpp:136-159); "j1 in free_cols" == y[j1] < 0 after greedy
                 for (int f = 0; f < n_free; ++f) {
@@ -972,10 +980,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
                     }
                     __syncthreads();
                 }
-                augment_all<MAXC, (MAXT > 512)>(S, n_free);
+                n_aug = n_free;
             }
         }
     }
+    __syncthreads();
+    if (n_aug > 0) augment_all<MAXC, (MAXT > 512)>(S, n_aug);
     __syncthreads();
     if (rc == 0) {
         for (int j = tid; j < n; j += T) {

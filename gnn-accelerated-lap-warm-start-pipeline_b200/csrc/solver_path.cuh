@@ -1,30 +1,39 @@
-// solver_path.cuh -- one shortest augmenting path (find_path_dense) with the Dijkstra state in REGISTERS.
+// solver_path.cuh -- one shortest augmenting path (find_path_dense) with the Dijkstra state in REGISTERS and
+// BATCHED relax steps over the SCAN queue.
 //
 // Reference: LAP/_lapjv_cpp/lapjv.cpp:153-171 (_find_dense), :178-213 (_scan_dense), :221-282 (find_path_dense).
 //
-// Layout.  A thread owns MAXC fixed columns for the whole path -- groups of VEC = 16 / sizeof(CT) consecutive
-// columns, one 128-bit load per group and matrix row -- and keeps their distance d and potential v in registers,
-// together with two bit masks: `todo` (the column is still in the TODO zone of cols[]) and `ready` (it was READY at
-// the last level collect, i.e. its potential moves at the end of the path).  A relax step (_scan_dense) is then
-//     1 row load per group  ->  cand = (c - v) - slack, compare with d, select   (no shared-memory read per column)
-// and the only things that leave the thread are the predecessor of an improved column (a predicated store) and the
-// rare hit (cand == level), published through a 3-slot rotating mailbox.  The common step -- exactly one hit -- is
-// finished by EVERY thread redundantly from the mailbox (hit column, its row y[j], its potential), so the next
-// row fetch is issued right after the step's single barrier; the swap of cols[]/pos[] that the reference performs
-// for the hit is done by thread 0 one step late, in the shadow of that fetch (nothing reads cols/pos in between:
-// hits are published by column, positions are only looked up after a barrier).  Steps with several hits, and the
-// level collects, keep the position bitmap + serial replay of solver.cuh (bit-exact order of cols[]).
-//
-// A level collect transposes d from column order (registers) to POSITION order (the shared array S.d is used as
-// d-by-position here), so that the prefix-minimum scan over positions [lo, n) reads consecutive words.
+// Measurements behind the design (B200, tools/micro/lat.cu, tools/batch_breakdown.py; profiles/r02_*):
+//   * a random 8 KB matrix row costs ~950 cycles from DRAM with 64 instances in flight, ~500 from L2;
+//   * the per-column arithmetic is pipe bound on ONE SM: F2F.F64.F32 16 lanes/clk, DSETP 32 lanes/clk, DADD 64 lanes/clk
+//     -> ~330 cycles per scanned row of n = 2048;
+//   * 60 % of the relax steps of the bench batch start with >= 5 columns already waiting in SCAN (the tight-edge
+//     search is wide: structural ties after every dual update), and a CTA barrier + shared-memory round trip is ~100.
+// So:
+//   * a thread owns MAXC fixed columns for the whole path -- groups of VEC = 16 / sizeof(CT) consecutive columns, one
+//     128-bit load per group and row -- with distance d and potential v in registers and two bit masks, `todo` (still
+//     in the TODO zone of cols[]) and `ready` (READY at the last level collect: its potential moves at the end);
+//   * a relax step takes up to KMAX columns from SCAN at once: their rows are fetched together (one memory latency),
+//     relaxed one after the other in registers (exactly the reference's sequential semantics per column: a column hit
+//     by an earlier scan of the batch has left TODO for the later ones), and all hits (cand == level) are published
+//     with (scan index, column, row y[j], potential) through a 3-slot rotating list;
+//   * after ONE barrier warp 0 replays the hits scan by scan, each scan's hits in ascending position order (positions
+//     are read after the swaps of the earlier scans) -- the first unmatched column ends the path exactly where the
+//     reference's early return does, later scans of the batch then never happened (their register updates are dead
+//     state: d/pred of TODO columns are re-initialised by the next path, READY columns are never touched);
+//   * every column that enters SCAN gets its queue entry (row, potential) written by position and its matrix row
+//     PREFETCHED INTO L2 (cp.async.bulk.prefetch.L2) -- the queue is deep, so by the time the row is scanned it is an
+//     L2 hit instead of a DRAM access;
+//   * a level collect transposes d from column order (registers) to POSITION order (the shared array `d`), flags the
+//     prefix-minimum records, and warp 0 replays them from (position, column, distance) tuples.
+// All state arrays are addressed as true shared memory here (the path is only taken when everything fits).
 #pragma once
 #include "common.cuh"
 
 namespace b200lap {
 
-// Measurement build only: step timings of two observer threads (thread 0 = the bookkeeping thread, thread 33 = an
-// ordinary one) in trace words 20 + 10 * observer + stamp.  A stamp is taken when `dep` is available (the predicate
-// makes the clock read wait for it).
+// Measurement build only: step timings of two observer threads (thread 0, thread 33) in trace words
+// 20 + 10 * observer + stamp.  A stamp is taken when `dep` is available (the predicate makes the clock read wait).
 #if defined(B200LAP_SOLVER_PROFILE) && !defined(B200LAP_EMUL)
 #define B200LAP_STAMP(idx, dep)                                                         \
     do {                                                                                \
@@ -38,22 +47,70 @@ namespace b200lap {
 #define B200LAP_STAMP(idx, dep) do { } while (0)
 #endif
 
+// L2 prefetch of one matrix row (bytes a multiple of 16, 16-byte aligned address)
+__device__ __forceinline__ void prefetch_row_l2(const void* p, unsigned bytes) {
+#ifndef B200LAP_EMUL
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+    (void)p; (void)bytes;
+#endif
+}
+
+// the state arrays as TRUE shared-memory pointers (same packing order as k_solve's placement with a full mask)
+struct SmemState {
+    unsigned int* bitmap;
+    double *d, *v;
+    int *pos, *y, *cols, *pred, *x, *free_rows, *srow;
+};
+__device__ __forceinline__ SmemState smem_state(unsigned char* dyn, int n) {
+    SmemState m;
+    size_t off = 0;
+    auto take = [&](int arr) { unsigned char* p = dyn + off; off += state_array_bytes(arr, n); return p; };
+    m.bitmap = (unsigned int*)take(ST_BITMAP);
+    m.d = (double*)take(ST_D);
+    m.pos = (int*)take(ST_POS);
+    m.v = (double*)take(ST_V);
+    m.y = (int*)take(ST_Y);
+    m.cols = (int*)take(ST_COLS);
+    m.pred = (int*)take(ST_PRED);
+    m.x = (int*)take(ST_X);
+    m.free_rows = (int*)take(ST_FREE);
+    m.srow = (int*)take(ST_SROW);
+    return m;
+}
+
+template <typename CT> struct PathCtx {
+    const CT* C;
+    int ld, n;
+    unsigned row_bytes;
+    SmemState m;
+    SolverShared* sh;
+};
+
+// a column enters SCAN at position k: queue entry + L2 prefetch of the row it will be scanned through
+template <typename CT>
+__device__ __forceinline__ void scan_enqueue(const PathCtx<CT>& P, int k, int yj, double vj) {
+    P.m.srow[k] = yj;
+    P.m.d[k] = vj;            // `d` holds distances by position only during a collect; positions in SCAN carry the potential
+    if (yj >= 0) prefetch_row_l2(P.C + (size_t)yj * P.ld, P.row_bytes);
+}
+
 // ---- serial replay of a level collect, d in POSITION order (warp 0) -------------------------------------------
 // The flagged positions (prefix-minimum records and ties, ascending) are turned into (position, column, distance)
 // tuples by the whole warp -- a record's position is not touched by the swaps of earlier records, so column and
-// distance can be fetched up front -- and lane 0 then replays the reference's swaps over the tuples with nothing
-// but one dependent shared-memory load per record on its chain (the next tuple is already in registers).
+// distance can be fetched up front -- and lane 0 then replays the reference's swaps over the tuples.
 template <typename CT>
-__device__ __forceinline__ void replay_collect_pos(SolverCtx<CT>& S, int lo, int wlo, int whi)
+__device__ __forceinline__ void replay_collect_pos(const PathCtx<CT>& P, int lo, int wlo, int whi)
 {
     const int lane = lane_id();
     const long long t0 = sm_clock();
-    SolverShared* sh = S.sh;
+    SolverShared* sh = P.sh;
+    const SmemState& m = P.m;
     int hi = lo, total = 0;
     double level = INFINITY;
     for (int w0 = wlo; w0 <= whi; w0 += 32) {
         unsigned int bits = 0;
-        if (w0 + lane <= whi) { bits = S.bitmap[w0 + lane]; if (bits) S.bitmap[w0 + lane] = 0u; }
+        if (w0 + lane <= whi) { bits = m.bitmap[w0 + lane]; if (bits) m.bitmap[w0 + lane] = 0u; }
         const int cnt = __popc(bits);
         int incl = cnt;
 #pragma unroll
@@ -72,21 +129,21 @@ __device__ __forceinline__ void replay_collect_pos(SolverCtx<CT>& S, int lo, int
                 ++idx;
             }
             __syncwarp();
-            const int m = min(kRecCap, round_total - c0);
-            for (int r = lane; r < m; r += 32) {
+            const int cntc = min(kRecCap, round_total - c0);
+            for (int r = lane; r < cntc; r += 32) {
                 const int k = sh->rec[r].k;
-                sh->rec[r].j = S.cols[k];
-                sh->rec[r].d = S.d[k];
+                sh->rec[r].j = m.cols[k];
+                sh->rec[r].d = m.d[k];
             }
             __syncwarp();
             if (lane == 0) {
                 RecTuple t = sh->rec[0];
-                for (int r = 0; r < m; ++r) {
-                    const RecTuple nx = sh->rec[r + 1 < m ? r + 1 : r];
+                for (int r = 0; r < cntc; ++r) {
+                    const RecTuple nx = sh->rec[r + 1 < cntc ? r + 1 : r];
                     if (t.d < level) { hi = lo; level = t.d; }
-                    const int c2 = S.cols[hi];
-                    S.cols[t.k] = c2; S.pos[c2] = t.k;
-                    S.cols[hi] = t.j; S.pos[t.j] = hi;
+                    const int c2 = m.cols[hi];
+                    m.cols[t.k] = c2; m.pos[c2] = t.k;
+                    m.cols[hi] = t.j; m.pos[t.j] = hi;
                     ++hi;
                     t = nx;
                 }
@@ -97,23 +154,106 @@ __device__ __forceinline__ void replay_collect_pos(SolverCtx<CT>& S, int lo, int
     }
     hi = __shfl_sync(kFull, hi, 0);
     if (hi == lo) hi = lo + 1;   // only reachable with NaN distances; keep moving
-    // unmatched column among the collected level: the LAST one in position order wins (lapjv.cpp:250-255)
+    // unmatched column among the collected level: the LAST one in position order wins (lapjv.cpp:250-255);
+    // every collected column gets its SCAN-queue entry
     int best = -1;
-    for (int k = lo + lane; k < hi; k += 32)
-        if (S.y[S.cols[k]] < 0) best = k;
+    for (int k = lo + lane; k < hi; k += 32) {
+        const int j = m.cols[k];
+        const int yj = m.y[j];
+        if (yj < 0) best = k;
+        scan_enqueue(P, k, yj, m.v[j]);
+    }
     best = warp_max_i(best);
     if (lane == 0) {
         sh->hi = hi;
-        sh->final_j = best >= 0 ? S.cols[best] : -1;
+        sh->final_j = best >= 0 ? m.cols[best] : -1;
         sh->level = level;
         B200LAP_PROF(sh->tr[TR_RECORDS] += total; sh->tr[TR_CYC_COLLECT_REPLAY] += sm_clock() - t0);
     }
 }
 
+// ---- replay of the hits of a batched relax step from the published list (warp 0, at most kHitCap hits) ---------
+// Scan by scan; within a scan ascending position (read after the swaps of the earlier scans); the first unmatched
+// column ends everything (lapjv.cpp:199-203).
+template <typename CT>
+__device__ __forceinline__ void replay_hits_list(const PathCtx<CT>& P, int hi_in, int K, int cnt, int slot)
+{
+    const int lane = lane_id();
+    SolverShared* sh = P.sh;
+    const SmemState& m = P.m;
+    HitEntry e;
+    e.sj = -1; e.yj = 0; e.v = 0.0;
+    if (lane < cnt) e = sh->hl[slot][lane];
+    const int my_s = e.sj >> 24;            // -1 for idle lanes
+    const int my_j = e.sj & 0xffffff;
+    int hi = hi_in, fin = -1, done = K;
+    for (int s = 0; s < K; ++s) {
+        unsigned mem = __ballot_sync(kFull, my_s == s);
+        if (!mem) continue;
+        __syncwarp();
+        int my_k = my_s == s ? m.pos[my_j] : 0x7fffffff;
+        while (mem) {
+            __syncwarp();
+            const int kmin = __reduce_min_sync(kFull, my_k);
+            const int src = __ffs((int)__ballot_sync(kFull, my_k == kmin)) - 1;
+            const int j = __shfl_sync(kFull, my_j, src);
+            const int yj = __shfl_sync(kFull, e.yj, src);
+            if (yj < 0) { fin = j; break; }
+            if (lane == src) {
+                const int c2 = m.cols[hi];
+                m.cols[kmin] = c2; m.pos[c2] = kmin;
+                m.cols[hi] = j; m.pos[j] = hi;
+                scan_enqueue(P, hi, yj, e.v);
+                my_k = 0x7fffffff;
+            }
+            ++hi;
+            mem &= ~(1u << src);
+        }
+        if (fin >= 0) { done = s + 1; break; }
+    }
+    __syncwarp();
+    if (lane == 0) { sh->hi = hi; sh->final_j = fin; sh->done_scans = done; }
+}
+
+// ---- replay of ONE scan's hits from the position bitmap (overflow path: more than kHitCap hits in a batch) ------
+template <typename CT>
+__device__ __forceinline__ void replay_hits_bitmap(const PathCtx<CT>& P, int hi_in, int wlo, int whi)
+{
+    const int lane = lane_id();
+    SolverShared* sh = P.sh;
+    const SmemState& m = P.m;
+    int hi = hi_in, fin = -1;
+    for (int w0 = wlo; w0 <= whi; w0 += 32) {
+        unsigned int bits = 0;
+        if (w0 + lane <= whi) { bits = m.bitmap[w0 + lane]; m.bitmap[w0 + lane] = 0u; }
+        unsigned int nz = __ballot_sync(kFull, bits != 0u);
+        while (nz) {
+            const int l = __ffs((int)nz) - 1;
+            nz &= nz - 1;
+            unsigned int word = __shfl_sync(kFull, bits, l);
+            if (lane == 0 && fin < 0) {
+                while (word) {
+                    const int bpos = __ffs((int)word) - 1;
+                    word &= word - 1;
+                    const int k = (w0 + l) * 32 + bpos;
+                    const int j = m.cols[k];
+                    const int yj = m.y[j];
+                    if (yj < 0) { fin = j; break; }
+                    const int c2 = m.cols[hi];
+                    m.cols[k] = c2; m.pos[c2] = k;
+                    m.cols[hi] = j; m.pos[j] = hi;
+                    scan_enqueue(P, hi, yj, m.v[j]);
+                    ++hi;
+                }
+            }
+        }
+    }
+    if (lane == 0) { sh->hi = hi; sh->final_j = fin; }
+}
+
 template <typename CT> struct VecOf;
 template <> struct VecOf<float> {
     static constexpr int V = 4;
-    typedef float4 type;
     static __device__ __forceinline__ void ld(const float* p, float* o) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(p));
         o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
@@ -131,7 +271,6 @@ template <> struct VecOf<float> {
 };
 template <> struct VecOf<double> {
     static constexpr int V = 2;
-    typedef double2 type;
     static __device__ __forceinline__ void ld(const double* p, double* o) {
         const double2 t = __ldg(reinterpret_cast<const double2*>(p));
         o[0] = t.x; o[1] = t.y;
@@ -148,17 +287,21 @@ template <> struct VecOf<double> {
     }
 };
 
-// Requires: n % VEC == 0, rows 16-byte aligned, blockDim.x * MAXC >= n, single CTA (S.nc == 1), all state arrays
-// addressable (shared or global -- only S.v, S.y are read and S.pred written per step, the rest at collects).
+// Requires: n % VEC == 0, rows 16-byte aligned, blockDim.x * MAXC >= n, single CTA, ALL state arrays in shared memory.
 template <int MAXC, typename CT>
 __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
 {
     typedef VecOf<CT> VT;
     constexpr int V = VT::V;
     constexpr int G = MAXC / V;
-    static_assert(MAXC % V == 0 && MAXC <= 32, "register-resident path: MAXC must be a multiple of the vector width");
+    constexpr int KMAX = MAXC >= 16 ? 1 : (16 / MAXC > 4 ? 4 : 16 / MAXC);    // scans per batch: KMAX * MAXC row entries in registers
+    static_assert(MAXC % V == 0 && MAXC <= 16, "register-resident path: MAXC must be a multiple of the vector width");
+    B200LAP_DYN_SMEM(dyn);
     const int n = S.n, T = blockDim.x, tid = threadIdx.x;
     SolverShared* sh = S.sh;
+    PathCtx<CT> P;
+    P.C = S.C; P.ld = S.ld; P.n = n; P.row_bytes = (unsigned)(n * sizeof(CT)); P.m = smem_state(dyn, n); P.sh = sh;
+    const SmemState& m = P.m;
     double dq[MAXC], vq[MAXC];
     unsigned todo = 0, ready = 0, valid = 0;
     // ---- start of the path: d = C[start] - v, identity permutation, every predecessor the root
@@ -174,10 +317,10 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
         for (int g = 0; g < G; ++g) {
             const int base = (g * T + tid) * V;
             if (base < n) {
-                VT::ld_d(S.v + base, &vq[g * V]);
-                VT::st_idx(S.cols + base, base);
-                VT::st_idx(S.pos + base, base);
-                VT::st_val(S.pred + base, start_i);
+                VT::ld_d(m.v + base, &vq[g * V]);
+                VT::st_idx(m.cols + base, base);
+                VT::st_idx(m.pos + base, base);
+                VT::st_val(m.pred + base, start_i);
                 valid |= ((1u << V) - 1u) << (g * V);
             } else {
 #pragma unroll
@@ -190,11 +333,7 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
     }
     int lo = 0, hi = 0, final_j = -1;
     double level = 0.0;
-    int js = 0, irow = 0;
-    double vjs = 0.0;
-    bool have_entry = false;
-    int pend_j = -1, pend_hi = 0;        // thread 0: the swap of the previous step's single hit, not yet applied
-    int n_collect = 0, n_relax = 0;      // thread 0: trace counters, flushed at the end of the path
+    int n_collect = 0, n_relax = 0;      // trace counters (uniform), flushed by thread 0 at the end of the path
 #if defined(B200LAP_SOLVER_PROFILE) && !defined(B200LAP_EMUL)
     const int obs = tid == 0 ? 0 : (tid == 33 ? 1 : -1);
     long long t_last = 0;
@@ -210,10 +349,10 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
                 const int base = (g * T + tid) * V;
                 if (base < n && ((todo >> (g * V)) & ((1u << V) - 1u))) {
                     int pk[V];
-                    VT::ld_idx(S.pos + base, pk);
+                    VT::ld_idx(m.pos + base, pk);
 #pragma unroll
                     for (int q = 0; q < V; ++q)
-                        if ((todo >> (g * V + q)) & 1u) S.d[pk[q]] = dq[g * V + q];
+                        if ((todo >> (g * V + q)) & 1u) m.d[pk[q]] = dq[g * V + q];
                 }
             }
             __syncthreads();
@@ -226,7 +365,7 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             double dch[MAXC];
             double lm = INFINITY;
 #pragma unroll
-            for (int q = 0; q < MAXC; ++q) dch[q] = (q < chunk && k0 + q < k1) ? S.d[k0 + q] : INFINITY;
+            for (int q = 0; q < MAXC; ++q) dch[q] = (q < chunk && k0 + q < k1) ? m.d[k0 + q] : INFINITY;
 #pragma unroll
             for (int q = 0; q < MAXC; ++q) lm = dch[q] < lm ? dch[q] : lm;
             double incl = lm;
@@ -254,7 +393,7 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             for (int q = 0; q < MAXC; ++q) {
                 if (q < chunk && k0 + q < k1 && dch[q] <= run) {
                     const int k = k0 + q;
-                    atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
+                    atomicOr(&m.bitmap[k >> 5], 1u << (k & 31));
                     wmin_i = min(wmin_i, k >> 5);
                     wmax_i = max(wmax_i, k >> 5);
                     run = dch[q];
@@ -271,7 +410,7 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
                     S.minw[old_slot] = 0x7fffffff; S.maxw[old_slot] = -1; S.nhit[old_slot] = 0;
                 }
                 if (whi < 0) { wlo = lo >> 5; whi = wlo; }
-                replay_collect_pos(S, lo, wlo, whi);
+                replay_collect_pos(P, lo, wlo, whi);
             }
             __syncthreads();
             B200LAP_PROF(if (tid == 0) sh->tr[39] += sm_clock() - tc3);
@@ -286,50 +425,56 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
                 if (((todo >> e) & 1u) && dq[e] == level) todo &= ~(1u << e);
             B200LAP_PROF(if (tid == 0) sh->tr[TR_CYC_COLLECT] += sm_clock() - tc0);
             if (final_j >= 0) break;
-            have_entry = false;
         }
-        // ================= one relax step (_scan_dense, one SCAN column) =================
+        // ================= one BATCHED relax step (_scan_dense over up to KMAX SCAN columns) =================
         const long long tr0 = sm_clock();
 #if defined(B200LAP_SOLVER_PROFILE) && !defined(B200LAP_EMUL)
         t_last = tr0;
 #endif
-        if (!have_entry) {
-            js = S.cols[lo];
-            irow = S.y[js];
-            vjs = S.v[js];
-        }
+        const int K = min(KMAX, hi - lo);
         const int sp = S.step % 3;
-        const CT* crow = S.C + (size_t)irow * S.ld;
-        B200LAP_STAMP(0, irow >= 0 && vjs == vjs);
-        CT cr[MAXC];
+        int ej[KMAX], er[KMAX];
+        double ev[KMAX];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const int base = (g * T + tid) * V;
-            if (base < n) VT::ld(crow + base, &cr[g * V]);
+        for (int s = 0; s < KMAX; ++s) {
+            const int k = lo + (s < K ? s : 0);
+            ej[s] = m.cols[k];
+            er[s] = m.srow[k];
+            ev[s] = m.d[k];
         }
-        const CT c_js = __ldg(crow + js);
-        if (tid == 0 && pend_j >= 0) {
-            // the reference's swap for the previous step's hit: cols[k] = cols[hi]; cols[hi++] = j
-            const int k = S.pos[pend_j];
-            const int c2 = S.cols[pend_hi];
-            S.cols[k] = c2; S.pos[c2] = k;
-            S.cols[pend_hi] = pend_j; S.pos[pend_j] = pend_hi;
-            pend_j = -1;
+        B200LAP_PROF(if (tid == 0) { const int dep_ = hi - lo; sh->tr[40 + (dep_ <= 1 ? 0 : dep_ == 2 ? 1 : dep_ <= 4 ? 2 : 3)] += 1; });
+        B200LAP_STAMP(0, er[0] >= 0 && ev[0] == ev[0]);
+        CT cr[KMAX][MAXC];
+        CT cjs[KMAX];
+#pragma unroll
+        for (int s = 0; s < KMAX; ++s) {
+            if (s < K) {
+                const CT* crow = S.C + (size_t)er[s] * S.ld;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int base = (g * T + tid) * V;
+                    if (base < n) VT::ld(crow + base, &cr[s][g * V]);
+                }
+                cjs[s] = __ldg(crow + ej[s]);
+            }
         }
-        B200LAP_STAMP(1, pend_j < 0);
-        const double slack = ((double)c_js - vjs) - level;
-        // profile build: word 13 = cycles until the row arrived (the slack needs c_js), word 14 = cycles in the barrier
-        B200LAP_PROF(if (tid == 0 && slack == slack) sh->tr[TR_CYC_ARR_SCAN] += sm_clock() - tr0);
-        B200LAP_STAMP(2, slack == slack);
+        B200LAP_STAMP(1, true);
         unsigned hitm = 0;
 #pragma unroll
-        for (int e = 0; e < MAXC; ++e) {
-            const int col = ((e / V) * T + tid) * V + (e % V);
-            const double cand = ((double)cr[e] - vq[e]) - slack;
-            if (((todo >> e) & 1u) && cand < dq[e]) {
-                dq[e] = cand;
-                S.pred[col] = irow;
-                if (cand == level) hitm |= 1u << e;
+        for (int s = 0; s < KMAX; ++s) {
+            if (s < K) {
+                const double slack = ((double)cjs[s] - ev[s]) - level;
+                if (s == 0) { B200LAP_STAMP(2, slack == slack); }
+#pragma unroll
+                for (int e = 0; e < MAXC; ++e) {
+                    const int col = ((e / V) * T + tid) * V + (e % V);
+                    const double cand = ((double)cr[s][e] - vq[e]) - slack;
+                    if (((todo >> e) & 1u) && cand < dq[e]) {
+                        dq[e] = cand;
+                        m.pred[col] = er[s];
+                        if (cand == level) { hitm |= 1u << (s * MAXC + e); todo &= ~(1u << e); }
+                    }
+                }
             }
         }
 #if defined(B200LAP_SOLVER_PROFILE) && !defined(B200LAP_EMUL)
@@ -340,64 +485,74 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             B200LAP_STAMP(3, acc_ == acc_ || hitm);
         }
 #endif
-        if (hitm) {
-            todo &= ~hitm;
-#pragma unroll
-            for (int e = 0; e < MAXC; ++e) {
-                if ((hitm >> e) & 1u) {
-                    const int col = ((e / V) * T + tid) * V + (e % V);
-                    if (atomicAdd(&S.nhit[sp], 1) == 0) {
-                        S.hit_j[sp] = col;
-                        sh->hit_y[sp] = S.y[col];
-                        sh->hit_v[sp] = vq[e];
-                    }
-                }
+        // publish the hits: (scan, column), the column's row and potential
+        for (unsigned hb = hitm; hb; hb &= hb - 1) {
+            const int b = __ffs((int)hb) - 1;
+            const int s = b / MAXC, e = b % MAXC;
+            const int col = ((e / V) * T + tid) * V + (e % V);
+            const int slot = atomicAdd(&S.nhit[sp], 1);
+            if (slot < kHitCap) {
+                HitEntry he;
+                he.sj = (s << 24) | col; he.yj = m.y[col]; he.v = m.v[col];
+                sh->hl[sp][slot] = he;
             }
         }
-        const long long tb0 = sm_clock();
         B200LAP_STAMP(4, true);
         __syncthreads();
         B200LAP_STAMP(5, true);
-        B200LAP_PROF(if (tid == 0) sh->tr[TR_CYC_ARR_SERIAL] += sm_clock() - tb0);
         S.step++;
-        const int nh = S.nhit[sp];
-        B200LAP_STAMP(6, nh >= 0);
+        const int cnt = S.nhit[sp];
         if (tid == 0) {
             const int old_slot = (sp + 2) % 3;
             S.minw[old_slot] = 0x7fffffff; S.maxw[old_slot] = -1; S.nhit[old_slot] = 0;
-            ++n_relax;
         }
-        ++lo;
-        have_entry = false;
-        if (nh == 1) {
-            const int j = S.hit_j[sp], yj = sh->hit_y[sp];
-            B200LAP_PROF(if (tid == 0) sh->tr[TR_RELAX_HITS] += 1);
-            if (yj < 0) { final_j = j; break; }
-            if (tid == 0) { pend_j = j; pend_hi = hi; }
-            if (lo == hi) { js = j; irow = yj; vjs = sh->hit_v[sp]; have_entry = true; }
-            ++hi;
-        } else if (nh > 1) {
-            // several hits: order them by position (bitmap) and replay serially, as the reference scans k ascending
-            int wmin_i = 0x7fffffff, wmax_i = -1;
-#pragma unroll
-            for (int e = 0; e < MAXC; ++e) {
-                if ((hitm >> e) & 1u) {
-                    const int col = ((e / V) * T + tid) * V + (e % V);
-                    const int k = S.pos[col];
-                    atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
-                    wmin_i = min(wmin_i, k >> 5);
-                    wmax_i = max(wmax_i, k >> 5);
-                }
-            }
-            if (wmax_i >= 0) { atomicMin(&S.minw[sp], wmin_i); atomicMax(&S.maxw[sp], wmax_i); }
-            __syncthreads();
-            if (warp_id() == 0) replay_relax(S, hi, S.minw[sp], S.maxw[sp]);
+        B200LAP_STAMP(6, cnt >= 0);
+        B200LAP_PROF(if (tid == 0) { sh->tr[44 + (cnt == 0 ? 0 : cnt == 1 ? 1 : 2)] += 1; if (cnt > 1) sh->tr[47] += cnt; });
+        if (cnt == 0) {
+            n_relax += K;
+            lo += K;
+        } else if (cnt <= kHitCap) {
+            if (warp_id() == 0) replay_hits_list(P, hi, K, cnt, sp);
             __syncthreads();
             hi = sh->hi;
             final_j = sh->final_j;
+            n_relax += sh->done_scans;
+            lo += K;
+            if (final_j >= 0) break;
+        } else {
+            // more hits than the list holds (tie-heavy instances): one scan at a time through the position bitmap
+            int hi_cur = hi, done = K;
+#pragma unroll 1
+            for (int s = 0; s < K; ++s) {
+                int wmin_i = 0x7fffffff, wmax_i = -1;
+                for (unsigned hb = (hitm >> (s * MAXC)) & ((1u << MAXC) - 1u); hb; hb &= hb - 1) {
+                    const int e = __ffs((int)hb) - 1;
+                    const int col = ((e / V) * T + tid) * V + (e % V);
+                    const int k = m.pos[col];
+                    atomicOr(&m.bitmap[k >> 5], 1u << (k & 31));
+                    wmin_i = min(wmin_i, k >> 5);
+                    wmax_i = max(wmax_i, k >> 5);
+                }
+                if (wmax_i >= 0) { atomicMin(&S.minw[sp], wmin_i); atomicMax(&S.maxw[sp], wmax_i); }
+                __syncthreads();
+                if (warp_id() == 0) {
+                    const int wlo = S.minw[sp], whi = S.maxw[sp];
+                    if (whi >= 0) replay_hits_bitmap(P, hi_cur, wlo, whi);
+                    else if (lane_id() == 0) { sh->hi = hi_cur; sh->final_j = -1; }
+                    __syncwarp();
+                    if (lane_id() == 0) { S.minw[sp] = 0x7fffffff; S.maxw[sp] = -1; }
+                }
+                __syncthreads();
+                hi_cur = sh->hi;
+                final_j = sh->final_j;
+                if (final_j >= 0) { done = s + 1; break; }
+            }
+            hi = hi_cur;
+            n_relax += done;
+            lo += K;
             if (final_j >= 0) break;
         }
-        B200LAP_STAMP(7, hi >= 0 && irow >= 0);
+        B200LAP_STAMP(7, hi >= 0);
         B200LAP_PROF(if (tid == 0) sh->tr[TR_CYC_RELAX] += sm_clock() - tr0);
     }
     // ---- dual update of the READY columns (lapjv.cpp:270-276): level == d[cols[n_ready]]
@@ -405,7 +560,7 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
     for (int e = 0; e < MAXC; ++e) {
         if ((ready >> e) & 1u) {
             const int col = ((e / V) * T + tid) * V + (e % V);
-            S.v[col] = vq[e] + (dq[e] - level);
+            m.v[col] = vq[e] + (dq[e] - level);
         }
     }
     if (tid == 0) { sh->tr[TR_COLLECT] += n_collect; sh->tr[TR_RELAX] += n_relax; }

@@ -21,7 +21,7 @@ extern "C" {
 #define B200LAP_ERR_ARG (-102)
 
 #define B200LAP_ROW_FEAT_DIM 21   /* gnn/features.py:223-241 */
-#define B200LAP_TRACE_WORDS 40
+#define B200LAP_TRACE_WORDS 48
 #define B200LAP_TOPK_MAX 32
 
 typedef struct b200lap_ctx b200lap_ctx;       /* one per (device, stream): workspaces + stream */

@@ -36,6 +36,7 @@ for reg in ([int(sys.argv[1])] if len(sys.argv) > 1 else [1, 0]):
         rs = max(1, t[9])
         names = ["addr(LDS chain)", "issue+swap", "row arrives(slack)", "compute 4 cols", "hit publish", "barrier", "nh read", "post"]
         cs = max(1, t[8])
+        print(f"  SCAN depth at step start: 1:{t[40]} 2:{t[41]} 3-4:{t[42]} 5+:{t[43]}   hits per step: 0:{t[44]} 1:{t[45]} 2+:{t[46]} (hits in those: {t[47]})")
         print(f"  collect (thread 0): transpose+bar={t[28]/cs:.0f} scan+bar={t[29]/cs:.0f} flags+bar={t[38]/cs:.0f} replay+bar={t[39]/cs:.0f}")
         for o, who in ((0, "thread 0"), (1, "thread 33")):
             print(f"  {who}: " + "  ".join(f"{names[k]}={t[20 + 10 * o + k] / rs:.0f}" for k in range(8)))
