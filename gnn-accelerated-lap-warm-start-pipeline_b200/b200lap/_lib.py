@@ -55,6 +55,10 @@ SIGNATURES = {
     "b200lap_model_destroy": (None, [vp]),
     "b200lap_compute_row_features": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "b200lap_pipeline_batch": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp, vp, vp, vp, vp]),
+    "b200lap_dev_project_feasible": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_double, vp]),
+    "b200lap_dev_reduced_costs": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]),
+    "b200lap_project_feasible": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_double, vp]),
+    "b200lap_reduce_costs": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp]),
     "b200lap_default_ctx": (vp, []),
 }
 

@@ -38,8 +38,10 @@ enum TraceSlot {
 
 struct RecTuple { int k, j; double d; };   // one record of a level collect: position, column, distance
 constexpr int kRecCap = 128;
-struct HitEntry { int sj, yj; double v; }; // one hit of a batched relax step: (scan index << 24 | column), its row, its potential
-constexpr int kHitCap = 32;
+struct HitEntry { int sj, yj; double v; }; // one hit of a batched relax step: column, the row matched to it, its potential
+struct HitResult { int hi, final_j, done, pad; };   // what the replay of a batch's hits found
+constexpr int kHitCap = 8;                 // hits per scan the lists hold (more: position-bitmap path)
+constexpr int kMaxScans = 4;               // scans per batched relax step
 
 struct SolverShared {
     BlockRed red;
@@ -53,8 +55,9 @@ struct SolverShared {
     double hit_v[3];
     double level;                      // register-resident path: the level a collect step ended with
     RecTuple rec[kRecCap];             // register-resident path: the records of a collect step, in position order
-    HitEntry hl[3][kHitCap];           // register-resident path: hits of a batched relax step (same 3-slot rotation as nhit)
-    int done_scans;                    // register-resident path: scans of the batch the reference would have performed
+    HitEntry hl[3][kMaxScans][kHitCap];   // register-resident path: hits of a batched relax step per scan (3-slot rotation as nhit)
+    int nh[3][kMaxScans];              // register-resident path: hits per scan
+    HitResult res[2];                  // register-resident path: replay results, double-buffered by batch parity
     int box_op, box_row, box_js, box_hi, box_sp;   // cluster mode: the master's command mailbox, read by the workers through DSMEM
     unsigned int cursor, deferred;
     int hitk[64];           // positions of the flagged records of a collect step, ascending
@@ -870,7 +873,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     if (S.rank != 0) { worker_loop(S); return; }
     if (tid == 0) {
         sh.s_cnt = 0;
-        for (int q = 0; q < 3; ++q) { S.minw[q] = 0x7fffffff; S.nhit[q] = 0; S.maxw[q] = -1; }
+        for (int q = 0; q < 3; ++q) { S.minw[q] = 0x7fffffff; S.nhit[q] = 0; S.maxw[q] = -1; for (int s2 = 0; s2 < kMaxScans; ++s2) sh.nh[q][s2] = 0; }
         for (int q = 0; q < kTraceWords; ++q) sh.tr[q] = 0;
     }
     for (int w = tid; w < (n + 31) / 32 + 4; w += T) S.bitmap[w] = 0u;

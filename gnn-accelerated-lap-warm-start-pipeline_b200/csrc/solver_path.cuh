@@ -172,31 +172,44 @@ __device__ __forceinline__ void replay_collect_pos(const PathCtx<CT>& P, int lo,
     }
 }
 
-// ---- replay of the hits of a batched relax step from the published list (warp 0, at most kHitCap hits) ---------
+// ---- replay of the hits of a batched relax step from the published per-scan lists (warp 0) ----------------------
 // Scan by scan; within a scan ascending position (read after the swaps of the earlier scans); the first unmatched
-// column ends everything (lapjv.cpp:199-203).
+// column ends everything (lapjv.cpp:199-203).  A scan with a single hit -- the common case -- needs no ordering at
+// all: every lane reads the same entry and lane 0 performs the swap.  Results go to sh->res[parity].
 template <typename CT>
-__device__ __forceinline__ void replay_hits_list(const PathCtx<CT>& P, int hi_in, int K, int cnt, int slot)
+__device__ __forceinline__ void replay_hits_list(const PathCtx<CT>& P, int hi_in, int K, int slot, int parity)
 {
     const int lane = lane_id();
     SolverShared* sh = P.sh;
     const SmemState& m = P.m;
-    HitEntry e;
-    e.sj = -1; e.yj = 0; e.v = 0.0;
-    if (lane < cnt) e = sh->hl[slot][lane];
-    const int my_s = e.sj >> 24;            // -1 for idle lanes
-    const int my_j = e.sj & 0xffffff;
     int hi = hi_in, fin = -1, done = K;
     for (int s = 0; s < K; ++s) {
-        unsigned mem = __ballot_sync(kFull, my_s == s);
-        if (!mem) continue;
+        const int c = sh->nh[slot][s];
+        if (c == 0) continue;
         __syncwarp();
-        int my_k = my_s == s ? m.pos[my_j] : 0x7fffffff;
-        while (mem) {
+        if (c == 1) {
+            const HitEntry e = sh->hl[slot][s][0];
+            const int j = e.sj;
+            if (e.yj < 0) { fin = j; done = s + 1; break; }
+            if (lane == 0) {
+                const int k = m.pos[j];
+                const int c2 = m.cols[hi];
+                m.cols[k] = c2; m.pos[c2] = k;
+                m.cols[hi] = j; m.pos[j] = hi;
+                scan_enqueue(P, hi, e.yj, e.v);
+            }
+            ++hi;
+            continue;
+        }
+        HitEntry e;
+        e.sj = 0; e.yj = 0; e.v = 0.0;
+        if (lane < c) e = sh->hl[slot][s][lane];
+        int my_k = lane < c ? m.pos[e.sj] : 0x7fffffff;
+        for (int q = 0; q < c; ++q) {
             __syncwarp();
             const int kmin = __reduce_min_sync(kFull, my_k);
             const int src = __ffs((int)__ballot_sync(kFull, my_k == kmin)) - 1;
-            const int j = __shfl_sync(kFull, my_j, src);
+            const int j = __shfl_sync(kFull, e.sj, src);
             const int yj = __shfl_sync(kFull, e.yj, src);
             if (yj < 0) { fin = j; break; }
             if (lane == src) {
@@ -207,12 +220,11 @@ __device__ __forceinline__ void replay_hits_list(const PathCtx<CT>& P, int hi_in
                 my_k = 0x7fffffff;
             }
             ++hi;
-            mem &= ~(1u << src);
         }
         if (fin >= 0) { done = s + 1; break; }
     }
     __syncwarp();
-    if (lane == 0) { sh->hi = hi; sh->final_j = fin; sh->done_scans = done; }
+    if (lane == 0) { sh->res[parity].hi = hi; sh->res[parity].final_j = fin; sh->res[parity].done = done; }
 }
 
 // ---- replay of ONE scan's hits from the position bitmap (overflow path: more than kHitCap hits in a batch) ------
@@ -334,11 +346,26 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
     int lo = 0, hi = 0, final_j = -1;
     double level = 0.0;
     int n_collect = 0, n_relax = 0;      // trace counters (uniform), flushed by thread 0 at the end of the path
+    // hits of the previous batch that warp 0 has not replayed yet (uniform): it replays them in the shadow of the NEXT
+    // batch's row fetch whenever SCAN still holds columns that were queued before
+    bool pend = false;
+    int pend_K = 0, pend_sp = 0, batch_no = 0;
 #if defined(B200LAP_SOLVER_PROFILE) && !defined(B200LAP_EMUL)
     const int obs = tid == 0 ? 0 : (tid == 33 ? 1 : -1);
     long long t_last = 0;
 #endif
     for (;;) {
+        if (lo == hi && pend) {
+            // SCAN ran dry: the pending hits decide how it goes on
+            if (warp_id() == 0) replay_hits_list(P, hi, pend_K, pend_sp, batch_no & 1);
+            __syncthreads();
+            const HitResult r = sh->res[batch_no & 1];
+            ++batch_no;
+            pend = false;
+            hi = r.hi;
+            n_relax += r.done;
+            if (r.final_j >= 0) { final_j = r.final_j; break; }
+        }
         if (lo == hi) {
             // ================= level collect (_find_dense) =================
             const long long tc0 = sm_clock();
@@ -408,6 +435,8 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
                 if (lane_id() == 0) {
                     const int old_slot = (sp + 2) % 3;
                     S.minw[old_slot] = 0x7fffffff; S.maxw[old_slot] = -1; S.nhit[old_slot] = 0;
+#pragma unroll
+                    for (int s = 0; s < kMaxScans; ++s) sh->nh[old_slot][s] = 0;
                 }
                 if (whi < 0) { wlo = lo >> 5; whi = wlo; }
                 replay_collect_pos(P, lo, wlo, whi);
@@ -459,6 +488,8 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             }
         }
         B200LAP_STAMP(1, true);
+        // the previous batch's hits: swaps, queue entries and row prefetches, while this batch's rows are in flight
+        if (pend && warp_id() == 0) replay_hits_list(P, hi, pend_K, pend_sp, batch_no & 1);
         unsigned hitm = 0;
 #pragma unroll
         for (int s = 0; s < KMAX; ++s) {
@@ -485,42 +516,49 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             B200LAP_STAMP(3, acc_ == acc_ || hitm);
         }
 #endif
-        // publish the hits: (scan, column), the column's row and potential
+        // publish the hits per scan: column, its row and its potential
         for (unsigned hb = hitm; hb; hb &= hb - 1) {
             const int b = __ffs((int)hb) - 1;
             const int s = b / MAXC, e = b % MAXC;
             const int col = ((e / V) * T + tid) * V + (e % V);
-            const int slot = atomicAdd(&S.nhit[sp], 1);
+            const int slot = atomicAdd(&sh->nh[sp][s], 1);
             if (slot < kHitCap) {
                 HitEntry he;
-                he.sj = (s << 24) | col; he.yj = m.y[col]; he.v = m.v[col];
-                sh->hl[sp][slot] = he;
+                he.sj = col; he.yj = m.y[col]; he.v = m.v[col];
+                sh->hl[sp][s][slot] = he;
             }
         }
         B200LAP_STAMP(4, true);
         __syncthreads();
         B200LAP_STAMP(5, true);
         S.step++;
-        const int cnt = S.nhit[sp];
+        int cnt = 0, cmax = 0;
+#pragma unroll
+        for (int s = 0; s < KMAX; ++s) { const int c = sh->nh[sp][s]; cnt += c; cmax = max(cmax, c); }
         if (tid == 0) {
             const int old_slot = (sp + 2) % 3;
             S.minw[old_slot] = 0x7fffffff; S.maxw[old_slot] = -1; S.nhit[old_slot] = 0;
+#pragma unroll
+            for (int s = 0; s < kMaxScans; ++s) sh->nh[old_slot][s] = 0;
         }
         B200LAP_STAMP(6, cnt >= 0);
         B200LAP_PROF(if (tid == 0) { sh->tr[44 + (cnt == 0 ? 0 : cnt == 1 ? 1 : 2)] += 1; if (cnt > 1) sh->tr[47] += cnt; });
+        if (pend) {
+            // what the replay of the previous batch found; if it ended the path, this batch never happened
+            const HitResult r = sh->res[batch_no & 1];
+            ++batch_no;
+            pend = false;
+            hi = r.hi;
+            n_relax += r.done;
+            if (r.final_j >= 0) { final_j = r.final_j; break; }
+        }
+        lo += K;
         if (cnt == 0) {
             n_relax += K;
-            lo += K;
-        } else if (cnt <= kHitCap) {
-            if (warp_id() == 0) replay_hits_list(P, hi, K, cnt, sp);
-            __syncthreads();
-            hi = sh->hi;
-            final_j = sh->final_j;
-            n_relax += sh->done_scans;
-            lo += K;
-            if (final_j >= 0) break;
+        } else if (cmax <= kHitCap) {
+            pend = true; pend_K = K; pend_sp = sp;
         } else {
-            // more hits than the list holds (tie-heavy instances): one scan at a time through the position bitmap
+            // more hits in one scan than its list holds (tie-heavy instances): one scan at a time through the position bitmap
             int hi_cur = hi, done = K;
 #pragma unroll 1
             for (int s = 0; s < K; ++s) {
@@ -549,7 +587,6 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             }
             hi = hi_cur;
             n_relax += done;
-            lo += K;
             if (final_j >= 0) break;
         }
         B200LAP_STAMP(7, hi >= 0);

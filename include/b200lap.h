@@ -110,6 +110,16 @@ int b200lap_dev_solve_cold(b200lap_ctx* ctx, const void* C, int is_f64, int batc
  * {any_violation, infeasible, total_tight lo, total_tight hi}. */
 int b200lap_dev_front_end(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const double* u_seed,
                           const double* v_seed, double eps, double* u_tight, int* tight_cnt, int* flags);
+/* solvers/advanced_dual.py:14-36 project_feasible on device buffers of one instance: u, v [n] binary64 are tightened in
+ * place (u = min(u, min_j(C - v)); v = min(v, min_i(C - u)); stop when no (c - u_i) - v_j < -tol, at most max_rounds
+ * rounds, at least one); *rounds (host, nullable) receives the rounds used. */
+int b200lap_dev_project_feasible(b200lap_ctx* ctx, const void* C, int is_f64, int n, double* u, double* v, int max_rounds,
+                                 double tol, int* rounds);
+/* solvers/advanced_dual.py:39-63: min_host[b] (HOST) = min_ij ((c_ij - u_i) - v_j) per instance -- the quantity
+ * check_dual_feasible tests and reduce_costs shifts by; out (device, nullable) [batch][n][n] receives the unshifted
+ * reduced-cost matrices (C - u 1^T) - 1 v^T. */
+int b200lap_dev_reduced_costs(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const double* u, const double* v,
+                              double* out, double* min_host);
 /* features -> OneGNN -> min-trick -> seeded solve without leaving the device. */
 int b200lap_dev_pipeline(b200lap_ctx* ctx, const b200lap_model* model, const void* C, int is_f64, int batch, int n,
                          double eps, int* x, int* y, int* rc, double* u64, double* v64, long long* trace);
@@ -134,6 +144,12 @@ int b200lap_compute_row_features(const double* C, int n, float* feat);
 /* predict + solve for a batch of host matrices [batch][n][n]; u,v nullable outputs [batch][n]. */
 int b200lap_pipeline_batch(const b200lap_model* model, const double* C, int batch, int n, double eps,
                            long long* x, long long* y, int* rc, double* u, double* v, long long* trace);
+/* solvers/advanced_dual.py:14-36 project_feasible(C, u, v, max_rounds, tol): u, v [n] updated in place. */
+int b200lap_project_feasible(const double* C, int n, double* u, double* v, int max_rounds, double tol, int* rounds);
+/* solvers/advanced_dual.py:39-53 reduce_costs(C, u, v, shift_nonneg) -> out [n][n] (nullable: then only *min_out, the
+ * minimum of the unshifted reduced costs, is produced -- what check_dual_feasible, :56-63, compares with -tol). */
+int b200lap_reduce_costs(const double* C, int n, const double* u, const double* v, int shift_nonneg, double* out,
+                         double* min_out);
 b200lap_ctx* b200lap_default_ctx(void);
 
 #ifdef __cplusplus

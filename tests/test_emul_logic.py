@@ -285,3 +285,30 @@ def test_row_features_warp_kernel(emu):
     assert lib.b200lap_dev_row_features(ctx, Cf.ctypes.data, 0, 1, n, 16, None, feat.ctypes.data, topv.ctypes.data) == 0
     feature_close(feat, ref, rtol=1e-4)
     assert np.array_equal(topv, np.sort(Cf, axis=1)[:, :16])
+
+
+def test_advanced_dual_sweeps(emu):
+    """solvers/advanced_dual.py:14-63 through the C ABI (project_feasible, reduce_costs / min reduced cost) against the
+    NumPy statements, bit for bit, binary32- and binary64-stored matrices."""
+    lib, ctx = emu
+    rng = np.random.default_rng(21)
+    for n, f64 in ((33, False), (48, False), (40, True)):
+        C = gen.make_instance("uniform", n, seed=n) if not f64 else rng.uniform(0, 1, (n, n))
+        u, v = noisy_oracle_seeds(C, 5e-2)
+        for rounds in (1, 50):
+            ur, vr = u.copy(), v.copy()
+            for _ in range(rounds):
+                ur = np.minimum(ur, (C - vr[None, :]).min(axis=1))
+                vr = np.minimum(vr, (C - ur[:, None]).min(axis=0))
+                if (C - ur[:, None] - vr[None, :]).min() >= -1e-12:
+                    break
+            ug, vg = u.copy(), v.copy()
+            used = ctypes.c_int(0)
+            assert lib.b200lap_project_feasible(C.ctypes.data, n, ug.ctypes.data, vg.ctypes.data, rounds, 1e-12, ctypes.addressof(used)) == 0
+            assert np.array_equal(ug, ur) and np.array_equal(vg, vr), (n, f64, rounds)
+        raw = C - u[:, None] - v[None, :]
+        out = np.empty((n, n)); mn = ctypes.c_double(0)
+        assert lib.b200lap_reduce_costs(C.ctypes.data, n, u.ctypes.data, v.ctypes.data, 1, out.ctypes.data, ctypes.addressof(mn)) == 0
+        assert mn.value == raw.min() and np.array_equal(out, raw - raw.min() if raw.min() < 0 else raw)
+        assert lib.b200lap_reduce_costs(C.ctypes.data, n, u.ctypes.data, v.ctypes.data, 0, None, ctypes.addressof(mn)) == 0
+        assert mn.value == raw.min()
