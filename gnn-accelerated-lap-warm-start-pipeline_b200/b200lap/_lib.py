@@ -11,6 +11,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200lap.so")
+if os.environ.get("B200LAP_LIB_VARIANT"):
+    LIB_PATH = os.path.join(_HERE, "libb200lap_" + os.environ["B200LAP_LIB_VARIANT"] + ".so")    # experiment builds (tools/)
 if os.environ.get("B200LAP_PROFILE_LIB") == "1":
     # measurement variant of the same sources (build.py --profile): SM-cycle counters in the solver trace; tools/ only
     LIB_PATH = os.path.join(_HERE, "libb200lap_prof.so")

@@ -55,6 +55,9 @@ def build(force: bool = False, verbose: bool = False, profile: bool = False) -> 
     if not force and not stale(out):
         return out
     prof = ["-DB200LAP_SOLVER_PROFILE"] if profile else []
+    if os.environ.get("B200LAP_KMAX"):       # experiment builds (tools/): scans per batched relax step
+        prof += ["-DB200LAP_KMAX=" + os.environ["B200LAP_KMAX"]]
+        out = out.replace(".so", "_k" + os.environ["B200LAP_KMAX"] + ".so")
     cmd = [nvcc_path()] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(CSRC, "api.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

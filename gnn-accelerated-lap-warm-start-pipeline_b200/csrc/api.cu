@@ -62,6 +62,8 @@ struct b200lap_ctx {
     int solver_cluster = 0;      // option: CTAs per instance (thread-block cluster), 0 = auto, 1 = single CTA
     int solver_cluster_min_n = 8192;   // option: auto mode uses a cluster from this size on
     int solver_regpath = 1;      // option: augmentation with register-resident d/v (solver_path.cuh); 0 = shared-memory state path
+    int solver_kcap = 0;         // option: scans per batched relax step of the register path (0 = auto)
+    int solver_pipe = 1;         // option: replay a batch's hits behind the next batch's row fetch
     int front_rows_per_cta = 0;  // option
     int mlp_impl = 0;            // option: 0 = default
     int feat_ept = 0;            // option: entries per thread of the row-feature kernel (0 = auto)
@@ -318,6 +320,7 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
     // 512-thread CTAs keep the per-thread state (4 registers per column) under the 128-register budget.
     a.regpath = (ctx->solver_regpath && cluster == 1 && vec_ok(C, inst_stride, ld, n)) ? 1 : 0;
     if (a.regpath && ctx->solver_threads <= 0 && T > 512 && n <= 8192) T = 512;
+    a.kcap = ctx->solver_kcap; a.pipe = ctx->solver_pipe;
     const int per_thread = (n + T - 1) / T;      // row entries a thread keeps in registers per step
 #define SOLVE(MAXC_)                                                                                                       \
     do {                                                                                                                   \
@@ -442,6 +445,8 @@ int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value) {
     else if (k == "solver_cluster") ctx->solver_cluster = (int)value;
     else if (k == "solver_cluster_min_n") ctx->solver_cluster_min_n = (int)value;
     else if (k == "solver_regpath") ctx->solver_regpath = (int)value;
+    else if (k == "solver_kcap") ctx->solver_kcap = (int)value;
+    else if (k == "solver_pipe") ctx->solver_pipe = (int)value;
     else if (k == "solver_smem_budget") ctx->max_dyn_smem = value > 0 ? (int)value : 227 * 1024 - 4096;
     else if (k == "front_rows_per_cta") ctx->front_rows_per_cta = (int)value;
     else if (k == "mlp_impl") ctx->mlp_impl = (int)value;

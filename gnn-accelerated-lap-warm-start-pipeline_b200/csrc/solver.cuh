@@ -41,7 +41,10 @@ constexpr int kRecCap = 128;
 struct HitEntry { int sj, yj; double v; }; // one hit of a batched relax step: column, the row matched to it, its potential
 struct HitResult { int hi, final_j, done, pad; };   // what the replay of a batch's hits found
 constexpr int kHitCap = 8;                 // hits per scan the lists hold (more: position-bitmap path)
-constexpr int kMaxScans = 4;               // scans per batched relax step
+#ifndef B200LAP_KMAX
+#define B200LAP_KMAX 4
+#endif
+constexpr int kMaxScans = B200LAP_KMAX;    // scans per batched relax step
 
 struct SolverShared {
     BlockRed red;
@@ -88,6 +91,8 @@ template <typename CT> struct SolveArgs {
     double* v_out;          // [B][n] final column potentials (nullable)
     int cluster;            // CTAs per instance (thread-block cluster size), 1 = single CTA
     int regpath;            // 1: augmentation keeps d/v in registers (solver_path.cuh); needs vector-aligned rows
+    int kcap;               // register path: scans per batched relax step (0 = as many as the registers hold)
+    int pipe;               // register path: replay a batch's hits behind the next batch's row fetch
 };
 
 // State arrays in placement priority order (hottest first): a relax step reads d, pos, v of every
@@ -182,6 +187,7 @@ template <typename CT> struct SolverCtx {
     int nc, rank;                              // thread-block cluster size and this CTA's rank (1, 0 without a cluster)
     unsigned msh;                              // cluster mode: shared::cluster address of the MASTER's SolverShared
     int regpath;                               // augmentation with register-resident d/v (solver_path.cuh)
+    int kcap, pipe;
 };
 
 // Cycle-level phase counters (trace words 11..19) are compiled in only with -DB200LAP_SOLVER_PROFILE
@@ -869,6 +875,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     S.rank = a.cluster > 1 ? (int)(blockIdx.x % (unsigned)a.cluster) : 0;
     S.msh = S.nc > 1 ? dsm_map(&sh, 0u) : 0u;
     S.regpath = (a.regpath && S.nc == 1 && a.smem_mask == (1 << ST_COUNT) - 1) ? 1 : 0;
+    S.kcap = a.kcap > 0 ? a.kcap : kMaxScans;
+    S.pipe = a.pipe;
     S.minw = sh.minw; S.maxw = sh.maxw; S.nhit = sh.nhit; S.hit_k = sh.hit_k; S.hit_j = sh.hit_j;
     if (S.rank != 0) { worker_loop(S); return; }
     if (tid == 0) {

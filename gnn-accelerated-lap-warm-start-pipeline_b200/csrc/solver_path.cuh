@@ -306,7 +306,7 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
     typedef VecOf<CT> VT;
     constexpr int V = VT::V;
     constexpr int G = MAXC / V;
-    constexpr int KMAX = MAXC >= 16 ? 1 : (16 / MAXC > 4 ? 4 : 16 / MAXC);    // scans per batch: KMAX * MAXC row entries in registers
+    constexpr int KMAX = (4 * kMaxScans) / MAXC > kMaxScans ? kMaxScans : ((4 * kMaxScans) / MAXC < 1 ? 1 : (4 * kMaxScans) / MAXC);    // scans per batch: KMAX * MAXC row entries in registers
     static_assert(MAXC % V == 0 && MAXC <= 16, "register-resident path: MAXC must be a multiple of the vector width");
     B200LAP_DYN_SMEM(dyn);
     const int n = S.n, T = blockDim.x, tid = threadIdx.x;
@@ -460,7 +460,7 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
 #if defined(B200LAP_SOLVER_PROFILE) && !defined(B200LAP_EMUL)
         t_last = tr0;
 #endif
-        const int K = min(KMAX, hi - lo);
+        const int K = min(min(KMAX, S.kcap), hi - lo);
         const int sp = S.step % 3;
         int ej[KMAX], er[KMAX];
         double ev[KMAX];
@@ -557,6 +557,16 @@ __device__ int shortest_path_reg(SolverCtx<CT>& S, int start_i)
             n_relax += K;
         } else if (cmax <= kHitCap) {
             pend = true; pend_K = K; pend_sp = sp;
+            if (!S.pipe) {
+                if (warp_id() == 0) replay_hits_list(P, hi, pend_K, pend_sp, batch_no & 1);
+                __syncthreads();
+                const HitResult r = sh->res[batch_no & 1];
+                ++batch_no;
+                pend = false;
+                hi = r.hi;
+                n_relax += r.done;
+                if (r.final_j >= 0) { final_j = r.final_j; break; }
+            }
         } else {
             // more hits in one scan than its list holds (tie-heavy instances): one scan at a time through the position bitmap
             int hi_cur = hi, done = K;
