@@ -73,7 +73,7 @@ def bench_config(world: int) -> dict:
     """The `config` object of both arms (the driver compares them key by key)."""
     return {"workload": f"{BATCH} mixed-family n={N_INST} instances per GPU (BASELINE configs[1], mid2048), random-init OneGNN h192/L4/k16",
             "families": list(FAMILIES), "storage": "binary32 C on the device (exact), binary64 solver arithmetic; binary64 on the host",
-            "l2": "inputs (1.07 GB/step) larger than L2", "parallelism": f"instance-sharded x{world}"}
+            "l2": "inputs (1.07 GB/step) larger than L2", "parallelism": f"instance-sharded x{world}", "steps_in_flight": 2}
 
 
 def named_state_dict():
@@ -286,31 +286,46 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # -- device-resident throughput
+    # -- device-resident throughput: two batches in flight (the context's two lanes alternate), so the SMs one
+    #    64-instance solve leaves idle (one CTA per instance, 148 SMs) work on the neighbouring step
     def step_resident():
         return ctx.pipeline(model, Cd)
 
+    ctx.set_overlap(True)
     for _ in range(args.warmup):
         out = step_resident()
     ctx.sync()
     barrier()
     launches0 = ctx.launches
+    outs = []
     with ClockSampler(local) as clk:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            out = step_resident()
-        e1.record(stream)
+            outs = (outs + [step_resident()])[-2:]
+        ctx.join()                      # lane 0's stream waits for lane 1 on the device ...
+        e1.record(stream)               # ... so this event closes the work of both lanes
         ctx.sync()
         barrier()
         ms_resident = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
-    rc = out[2].cpu().numpy()
-    assert (rc == 0).all(), rc
+    ctx.set_overlap(False)
+    out = outs[-1]
+    for o in outs:
+        assert (o[2].cpu().numpy() == 0).all(), o[2]
+        assert torch.equal(o[0], out[0]) and torch.equal(o[1], out[1]), "the two lanes disagree"
     t = torch.tensor([ms_resident], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
+    # one batch at a time (latency of a step when nothing else is in flight)
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record(stream)
+    for _ in range(3):
+        step_resident()
+    eb.record(stream)
+    ctx.sync()
+    ms_step_alone = ea.elapsed_time(eb) / 3
 
     # -- per-kernel dense pass (CUDA events on the launching stream), same resident batch
     u = torch.zeros((B, n), dtype=torch.float32, device="cuda")
@@ -365,38 +380,44 @@ def run_b200(args):
         except Exception as exc:  # noqa: BLE001
             big = {"error": repr(exc)}
 
-    # -- end to end through the host-buffer C ABI (pinned host float64 in, host int64 out)
-    lib = ctx.lib
-    xh = torch.empty((B, n), dtype=torch.int64).pin_memory()
-    yh = torch.empty((B, n), dtype=torch.int64).pin_memory()
-    rch = np.zeros(B, dtype=np.int32)
-    # the host entry points use the library's default context; make it this rank's device
-    torch.cuda.set_device(local)
-    import ctypes
-    from b200lap.runtime import pack_state_dict
-    dctx = lib.b200lap_default_ctx()
-    blob, in_dim, hidden, layers = pack_state_dict(named_state_dict())
-    hmodel = ctypes.c_void_p()
-    assert lib.b200lap_model_create(dctx, blob.ctypes.data, blob.size, in_dim, hidden, layers, 16, ctypes.byref(hmodel)) == 0
+    # -- end to end through the host-buffer C ABI (pinned host float64 in, host int64 out), two batches in flight:
+    #    b200lap_pipeline_batch_submit / _wait; every step uploads its 2 GiB of binary64 matrices and downloads its
+    #    assignments inside the timed region, the upload of step k+1 overlaps the solve of step k
+    torch.cuda.set_device(local)          # the host entry points use the library's default context: make it this rank's device
+    hp = b200lap.HostPipeline(named_state_dict(), topk=16)
+    hbuf = [(torch.empty((B, n), dtype=torch.int64).pin_memory(), torch.empty((B, n), dtype=torch.int64).pin_memory(),
+             np.zeros(B, dtype=np.int32)) for _ in range(2)]
 
-    def step_e2e():
-        r = lib.b200lap_pipeline_batch(hmodel, Cp.data_ptr(), B, n, 1e-12, xh.data_ptr(), yh.data_ptr(), rch.ctypes.data, None, None, None)
-        assert r == 0 and (rch == 0).all(), (r, b200lap._lib.last_error(lib))
+    def run_e2e(steps):
+        pending = []
+        for s_ in range(steps):
+            xh_, yh_, rc_ = hbuf[s_ % 2]
+            pending.append(hp.submit(Cp, xh_, yh_, rc_))
+            if len(pending) == 2:
+                hp.wait(pending.pop(0))
+        while pending:
+            hp.wait(pending.pop(0))
 
-    e2e_steps = max(1, min(args.steps, 3))
-    step_e2e()
+    e2e_steps = max(2, args.steps)
+    run_e2e(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
+    run_e2e(e2e_steps)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
-    # resident and host paths must agree bit for bit
+    # the synchronous single-call form of the same path (b200lap_pipeline_batch), one batch at a time
+    xh, yh, rch = hbuf[0]
+    t0 = time.perf_counter()
+    hp.run(Cp, xh, yh, rch)
+    e2e_sync_s = time.perf_counter() - t0
+    assert (rch == 0).all() and (hbuf[1][2] == 0).all()
+    # resident, asynchronous and synchronous host paths must agree bit for bit
     assert np.array_equal(out[0].cpu().numpy().astype(np.int64), xh.numpy()), "host and resident paths disagree"
+    assert np.array_equal(hbuf[1][0].numpy(), xh.numpy()) and np.array_equal(hbuf[1][1].numpy(), yh.numpy()), "asynchronous host path disagrees"
 
     if rank == 0:
         peak, which = load_peaks()
@@ -423,11 +444,13 @@ def run_b200(args):
                                                    "mean_latency_s": round(float(np.mean(sper)), 3)}}
         line = {
             "metric": METRIC, "value": round(world * B / (ms_step * 1e-3), 2), "unit": "instances/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "ms_per_step_alone": round(ms_step_alone, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": bench_config(world),
             "e2e": {"value": round(world * B / e2e_s, 2), "unit": "instances/s", "h2d_bytes_per_step": int(Ch.nbytes),
-                    "d2h_bytes_per_step": int(B * n * 4 * 2 + rch.nbytes), "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(B * n * 8 * 2 + rch.nbytes + 4), "steps": e2e_steps,
+                    "api": "b200lap_pipeline_batch_submit/_wait, two batches in flight",
+                    "one_batch_at_a_time": {"value": round(world * B / e2e_sync_s, 2), "unit": "instances/s", "api": "b200lap_pipeline_batch"}},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "kernel": "row-feature sweep: k_row_features_warp + the redo pass of k_row_features_smem (21-D features + top-16, one read of C)", "achieved": achieved,

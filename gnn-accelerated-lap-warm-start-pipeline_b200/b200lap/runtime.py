@@ -253,20 +253,101 @@ class Context:
         total = (fl[:, 2].to(torch.int64) & 0xFFFFFFFF) | (fl[:, 3].to(torch.int64) << 32)
         return ut, tc, fl[:, 0] != 0, fl[:, 1] != 0, total
 
-    @_ordered
     def pipeline(self, model: "Model", C, eps: float = 1e-12, want_trace: bool = False):
-        """features -> OneGNN -> min-trick -> seeded JV without leaving the device."""
+        """features -> OneGNN -> min-trick -> seeded JV without leaving the device.
+
+        With ``set_overlap(True)`` consecutive calls alternate between the context's two lanes (two independent batches
+        in flight: a 64-instance solve occupies 64 of the 148 SMs); the returned tensors are then complete only after
+        ``sync()`` -- or, for work on torch's current stream, after ``join()`` + ``wait_for_context()``."""
         torch = _torch()
-        C, f64, B, n = self._matrix_args(C)
-        x = torch.full((B, n), -1, dtype=torch.int32, device=C.device)
-        y = torch.full((B, n), -1, dtype=torch.int32, device=C.device)
-        rc = self._empty((B,), torch.int32)
-        u64 = self._empty((B, n), torch.float64)
-        v64 = self._empty((B, n), torch.float64)
-        tr = self._empty((B, TRACE_WORDS), torch.int64) if want_trace else None
-        check(self.lib.b200lap_dev_pipeline(self.handle, model.handle, ptr(C), f64, B, n, float(eps), ptr(x), ptr(y), ptr(rc), ptr(u64), ptr(v64), ptr(tr)),
-              "b200lap_dev_pipeline", self.lib)
+        cur = torch.cuda.current_stream(self.device)
+        overlap = getattr(self, "_overlap", False)
+        lanes = [self.lane_stream(0), self.lane_stream(1)] if overlap else [self.torch_stream()]
+        for st in lanes:
+            if cur.cuda_stream != st.cuda_stream:
+                st.wait_stream(cur)                     # C (and the model) are complete before our kernels read them
+        with torch.cuda.device(self.device):
+            C, f64, B, n = self._matrix_args(C)
+            x = torch.full((B, n), -1, dtype=torch.int32, device=C.device)
+            y = torch.full((B, n), -1, dtype=torch.int32, device=C.device)
+            rc = self._empty((B,), torch.int32)
+            u64 = self._empty((B, n), torch.float64)
+            v64 = self._empty((B, n), torch.float64)
+            tr = self._empty((B, TRACE_WORDS), torch.int64) if want_trace else None
+            if overlap:
+                for st in lanes:                         # the fills above ran on torch's current stream
+                    st.wait_stream(cur)
+            check(self.lib.b200lap_dev_pipeline(self.handle, model.handle, ptr(C), f64, B, n, float(eps), ptr(x), ptr(y), ptr(rc), ptr(u64), ptr(v64), ptr(tr)),
+                  "b200lap_dev_pipeline", self.lib)
+        if not overlap and cur.cuda_stream != lanes[0].cuda_stream:
+            cur.wait_stream(lanes[0])
         return (x, y, rc, u64, v64, tr) if want_trace else (x, y, rc, u64, v64)
+
+    # ---- two batches in flight ------------------------------------------------------------------------------
+    def lane_stream(self, lane: int):
+        torch = _torch()
+        if getattr(self, "_lanes", None) is None:
+            self._lanes = [torch.cuda.ExternalStream(int(self.lib.b200lap_ctx_lane_stream(self.handle, k) or 0), device=self.device)
+                           for k in (0, 1)]
+        return self._lanes[lane]
+
+    def set_overlap(self, on: bool):
+        """Alternate whole-pipeline calls between the two lanes (see ``pipeline``)."""
+        self._overlap = bool(on)
+        self.set_option("overlap_steps", 1 if on else 0)
+
+    def join(self):
+        """Lane 0's stream (``torch_stream()``) waits on the device for everything enqueued on lane 1."""
+        check(self.lib.b200lap_ctx_join(self.handle), "b200lap_ctx_join", self.lib)
+
+
+class HostPipeline:
+    """Throughput form of the host-buffer pipeline (``b200lap_pipeline_batch_submit`` / ``_wait``): keep two batches
+    in flight so that the upload and dense pass of one overlap the solve of the other.
+
+        hp = HostPipeline(state_dict)
+        t = hp.submit(C_pinned_f64, x_i64, y_i64, rc_i32)      # returns at once
+        ...
+        hp.wait(t)                                              # x, y, rc are complete
+    """
+
+    def __init__(self, state_dict: Mapping, topk: int = 16):
+        self.lib = _lib.load()
+        self.ctx = self.lib.b200lap_default_ctx()
+        if not self.ctx:
+            raise B200LapError("no CUDA device is visible: b200lap has no CPU path")
+        blob, in_dim, hidden, layers = pack_state_dict(state_dict)
+        h = ctypes.c_void_p()
+        check(self.lib.b200lap_model_create(self.ctx, blob.ctypes.data, blob.size, in_dim, hidden, layers, int(topk), ctypes.byref(h)),
+              "b200lap_model_create", self.lib)
+        self.model = h
+
+    def submit(self, C, x, y, rc, eps: float = 1e-12):
+        B, n = int(C.shape[0]), int(C.shape[1])
+        job = ctypes.c_void_p()
+        check(self.lib.b200lap_pipeline_batch_submit(self.model, ptr(C), B, n, float(eps), ptr(x), ptr(y), ptr(rc), ctypes.byref(job)),
+              "b200lap_pipeline_batch_submit", self.lib)
+        return job
+
+    def wait(self, job):
+        check(self.lib.b200lap_pipeline_batch_wait(job), "b200lap_pipeline_batch_wait", self.lib)
+
+    def run(self, C, x, y, rc, eps: float = 1e-12):
+        """One synchronous batch (``b200lap_pipeline_batch``)."""
+        B, n = int(C.shape[0]), int(C.shape[1])
+        check(self.lib.b200lap_pipeline_batch(self.model, ptr(C), B, n, float(eps), ptr(x), ptr(y), ptr(rc), None, None, None),
+              "b200lap_pipeline_batch", self.lib)
+
+    def close(self):
+        if getattr(self, "model", None):
+            self.lib.b200lap_model_destroy(self.model)
+            self.model = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Model:

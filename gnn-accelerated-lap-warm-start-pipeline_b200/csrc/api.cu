@@ -4,6 +4,7 @@
 // computes on the host.  Built by nvcc only (build.py); the same translation unit also compiles
 // against tests/emul/cuda_emul.h for the CPU-side logic tests (test infrastructure, not shipped).
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -73,9 +74,22 @@ struct b200lap_ctx {
     int feat_nsamp = 0;
     int feat_ctas = 0;
     int sm_count = 148;
-    float* posenc = nullptr;     // cached positional-encoding table [posenc_n][8]
-    int posenc_n = 0;
+    std::map<int, float*> posenc;   // positional-encoding tables [n][8], one per n ever used (never freed before the ctx)
     std::mutex mu;
+    // Second LANE (its own stream and workspace blocks): independent whole-pipeline calls alternate between the two
+    // lanes when `overlap_steps` is on, so two batches are in flight and the SMs a 64-instance batch leaves idle
+    // (one CTA per instance) work on the other batch.  `stream` / `blocks` always name the ACTIVE lane; outside a
+    // call that is lane 0.
+    cudaStream_t stream2 = nullptr;
+    std::vector<WsBlock> blocks2;
+    cudaEvent_t lane_ev = nullptr;
+    int active_lane = 0;
+    int overlap_steps = 0;       // option: b200lap_dev_pipeline / pipeline_batch_submit alternate lanes
+    long long lane_calls = 0;
+    void use_lane(int l) {
+        if (l != active_lane) { std::swap(stream, stream2); std::swap(blocks, blocks2); active_lane = l; }
+    }
+    cudaStream_t lane_stream(int l) const { return l == active_lane ? stream : stream2; }
 
     void ws_reset() {
         for (auto& b : blocks) b.off = 0;
@@ -91,9 +105,10 @@ struct b200lap_ctx {
         size_t sz = bytes > ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
         void* p = nullptr;
         if (cudaMalloc(&p, sz) != cudaSuccess) {
+            (void)cudaGetLastError();      // a failed cudaMalloc leaves the error set: do not let a later launch check see it
             // a smaller exact-size block may still fit
             sz = bytes;
-            if (cudaMalloc(&p, sz) != cudaSuccess) return nullptr;
+            if (cudaMalloc(&p, sz) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
         }
         blocks.push_back(WsBlock{(unsigned char*)p, sz, bytes});
         return p;
@@ -264,14 +279,22 @@ cudaError_t launch_clustered(K kernel, int batch, int cluster, int T, size_t sme
 
 template <typename CT>
 int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int batch, int n, const double* u_seed,
-              const double* v_seed, double eps, int mode, int* x, int* y, int* rc, long long* trace, double* v_out)
+              const double* v_seed, double eps, int mode, int* x, int* y, int* rc, long long* trace, double* v_out,
+              const CT* colmin_in = nullptr, const int* colarg_in = nullptr)
 {
     if (batch <= 0) return 0;
     if (n <= 0) return fail(-2, "n <= 0");
-    TAKE(colmin, CT, (size_t)batch * n);
-    TAKE(colarg, int, (size_t)batch * n);
-    int r = run_col_argmin(ctx, C, inst_stride, ld, batch, n, colmin, colarg);
-    if (r) return r;
+    // column minima + first rows: handed over by the dense pass when it ran on the same matrices (no fifth sweep of C)
+    const CT* colmin = colmin_in;
+    const int* colarg = colarg_in;
+    int r = 0;
+    if (!colmin || !colarg) {
+        TAKE(cm, CT, (size_t)batch * n);
+        TAKE(ca, int, (size_t)batch * n);
+        r = run_col_argmin(ctx, C, inst_stride, ld, batch, n, cm, ca);
+        if (r) return r;
+        colmin = cm; colarg = ca;
+    }
     SolveArgs<CT> a;
     a.C = C; a.inst_stride = inst_stride; a.ld = ld; a.n = n;
     a.u_seed = u_seed; a.v_seed = v_seed; a.eps = eps; a.mode = mode;
@@ -356,9 +379,11 @@ __global__ void k_narrow(const double* __restrict__ src, long long count, float*
     if (bad) atomicAnd(exact, 0);
 }
 
-__global__ void k_widen_ids(const int* __restrict__ src, long long count, long long* __restrict__ dst) {
+// int32 assignments -> int64 (the reference's long long x, y); rows of instances with rc != 0 read -1
+__global__ void k_widen_ids(const int* __restrict__ src, const int* __restrict__ rc, int n, long long count, long long* __restrict__ dst) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[i] = (long long)src[i];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        dst[i] = rc[i / n] == 0 ? (long long)src[i] : -1ll;
 }
 
 int run_narrow(b200lap_ctx* ctx, const double* src, long long count, float* dst, int* exact) {
@@ -413,6 +438,12 @@ int b200lap_ctx_create(int device, void* stream, b200lap_ctx** out) {
         if (e != cudaSuccess) { delete c; return fail(B200LAP_ERR_CUDA, "cudaStreamCreate failed"); }
         c->own_stream = true;
     }
+    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->lane_ev, cudaEventDisableTiming) != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete c;
+        return fail(B200LAP_ERR_CUDA, "cudaStreamCreate failed (second lane)");
+    }
     *out = c;
     return 0;
 }
@@ -420,18 +451,33 @@ int b200lap_ctx_create(int device, void* stream, b200lap_ctx** out) {
 void b200lap_ctx_destroy(b200lap_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    ctx->use_lane(0);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     for (auto& b : ctx->blocks) cudaFree(b.p);
-    if (ctx->posenc) cudaFree(ctx->posenc);
+    for (auto& b : ctx->blocks2) cudaFree(b.p);
+    for (auto& kv : ctx->posenc) cudaFree(kv.second);
+    if (ctx->lane_ev) cudaEventDestroy(ctx->lane_ev);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
-void* b200lap_ctx_stream(b200lap_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+void* b200lap_ctx_stream(b200lap_ctx* ctx) { return ctx ? (void*)ctx->lane_stream(0) : nullptr; }
+void* b200lap_ctx_lane_stream(b200lap_ctx* ctx, int lane) { return ctx ? (void*)ctx->lane_stream(lane ? 1 : 0) : nullptr; }
 
 int b200lap_ctx_sync(b200lap_ctx* ctx) {
     if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->lane_stream(0)));
+    CK(cudaStreamSynchronize(ctx->lane_stream(1)));
+    return 0;
+}
+
+/* lane 0's stream waits (on the device) for everything enqueued on lane 1 so far */
+int b200lap_ctx_join(b200lap_ctx* ctx) {
+    if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
+    CK(cudaEventRecord(ctx->lane_ev, ctx->lane_stream(1)));
+    CK(cudaStreamWaitEvent(ctx->lane_stream(0), ctx->lane_ev, 0));
     return 0;
 }
 
@@ -447,6 +493,7 @@ int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value) {
     else if (k == "solver_regpath") ctx->solver_regpath = (int)value;
     else if (k == "solver_kcap") ctx->solver_kcap = (int)value;
     else if (k == "solver_pipe") ctx->solver_pipe = (int)value;
+    else if (k == "overlap_steps") ctx->overlap_steps = (int)value;
     else if (k == "solver_smem_budget") ctx->max_dyn_smem = value > 0 ? (int)value : 227 * 1024 - 4096;
     else if (k == "front_rows_per_cta") ctx->front_rows_per_cta = (int)value;
     else if (k == "mlp_impl") ctx->mlp_impl = (int)value;

@@ -26,6 +26,7 @@ extern "C" {
 
 typedef struct b200lap_ctx b200lap_ctx;       /* one per (device, stream): workspaces + stream */
 typedef struct b200lap_model b200lap_model;   /* OneGNN weights packed on a device              */
+typedef struct b200lap_job b200lap_job;       /* one batch submitted to the asynchronous host-buffer pipeline */
 
 /* ------------------------------------------------------------------------------------------
  * 1. Drop-in: the reference's only extern "C" symbol.
@@ -58,7 +59,13 @@ int b200lap_lapjv_seeded_batch(const double* C, int batch, int n, long long* x, 
 int b200lap_ctx_create(int device, void* stream, b200lap_ctx** out);
 void b200lap_ctx_destroy(b200lap_ctx* ctx);
 void* b200lap_ctx_stream(b200lap_ctx* ctx);          /* the cudaStream_t work is enqueued on */
-int b200lap_ctx_sync(b200lap_ctx* ctx);
+int b200lap_ctx_sync(b200lap_ctx* ctx);               /* waits for both lanes */
+/* A context has two LANES (stream + workspace each).  With the option overlap_steps = 1, consecutive
+ * b200lap_dev_pipeline calls alternate between them, so two independent batches are in flight (a 64-instance solve
+ * occupies 64 of the 148 SMs).  Results of such calls are complete after b200lap_ctx_sync, or -- for work enqueued on
+ * lane 0's stream -- after b200lap_ctx_join, which makes lane 0's stream wait for lane 1 on the device. */
+void* b200lap_ctx_lane_stream(b200lap_ctx* ctx, int lane);
+int b200lap_ctx_join(b200lap_ctx* ctx);
 /* Tuning / test options (0 = automatic unless stated): solver_threads, solver_cluster (CTAs per instance: 1 = single
  * CTA, 2/4/8 = thread-block cluster; auto = 8 from solver_cluster_min_n = 8192 on), force_global_state,
  * solver_smem_budget, front_rows_per_cta, mlp_impl (1 = FFMA instead of tcgen05), feat_impl (1 = register-resident
@@ -150,6 +157,13 @@ int b200lap_project_feasible(const double* C, int n, double* u, double* v, int m
  * minimum of the unshifted reduced costs, is produced -- what check_dual_feasible, :56-63, compares with -tol). */
 int b200lap_reduce_costs(const double* C, int n, const double* u, const double* v, int shift_nonneg, double* out,
                          double* min_out);
+/* Asynchronous form of b200lap_pipeline_batch for throughput: submit() enqueues upload, pipeline and download on one of
+ * the default context's two lanes and returns at once (pass pinned host memory for C, or the upload blocks); wait()
+ * blocks until that batch is complete, writes x, y [batch][n] (rows of instances with rc != 0 read -1) and rc, and
+ * frees the job.  At most two batches may be outstanding (one per lane): submit k+2 needs wait k first. */
+int b200lap_pipeline_batch_submit(const b200lap_model* model, const double* C, int batch, int n, double eps, long long* x,
+                                  long long* y, int* rc, b200lap_job** job);
+int b200lap_pipeline_batch_wait(b200lap_job* job);
 b200lap_ctx* b200lap_default_ctx(void);
 
 #ifdef __cplusplus
