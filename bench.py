@@ -73,7 +73,7 @@ def bench_config(world: int) -> dict:
     """The `config` object of both arms (the driver compares them key by key)."""
     return {"workload": f"{BATCH} mixed-family n={N_INST} instances per GPU (BASELINE configs[1], mid2048), random-init OneGNN h192/L4/k16",
             "families": list(FAMILIES), "storage": "binary32 C on the device (exact), binary64 solver arithmetic; binary64 on the host",
-            "l2": "inputs (1.07 GB/step) larger than L2", "parallelism": f"instance-sharded x{world}", "steps_in_flight": 2}
+            "l2": "inputs (1.07 GB/step) larger than L2", "parallelism": f"instance-sharded x{world}", "steps_in_flight": int(os.environ.get("B200LAP_LANES", "2"))}
 
 
 def named_state_dict():
@@ -291,7 +291,8 @@ def run_b200(args):
     def step_resident():
         return ctx.pipeline(model, Cd)
 
-    ctx.set_overlap(True)
+    LANES = int(os.environ.get("B200LAP_LANES", "2"))
+    ctx.set_overlap(LANES)
     for _ in range(args.warmup):
         out = step_resident()
     ctx.sync()
@@ -302,7 +303,7 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            outs = (outs + [step_resident()])[-2:]
+            outs = (outs + [step_resident()])[-LANES:]
         ctx.join()                      # lane 0's stream waits for lane 1 on the device ...
         e1.record(stream)               # ... so this event closes the work of both lanes
         ctx.sync()
@@ -384,22 +385,22 @@ def run_b200(args):
     #    b200lap_pipeline_batch_submit / _wait; every step uploads its 2 GiB of binary64 matrices and downloads its
     #    assignments inside the timed region, the upload of step k+1 overlaps the solve of step k
     torch.cuda.set_device(local)          # the host entry points use the library's default context: make it this rank's device
-    hp = b200lap.HostPipeline(named_state_dict(), topk=16)
+    hp = b200lap.HostPipeline(named_state_dict(), topk=16, lanes=LANES)
     hbuf = [(torch.empty((B, n), dtype=torch.int64).pin_memory(), torch.empty((B, n), dtype=torch.int64).pin_memory(),
-             np.zeros(B, dtype=np.int32)) for _ in range(2)]
+             np.zeros(B, dtype=np.int32)) for _ in range(LANES)]
 
     def run_e2e(steps):
         pending = []
         for s_ in range(steps):
-            xh_, yh_, rc_ = hbuf[s_ % 2]
+            xh_, yh_, rc_ = hbuf[s_ % LANES]
             pending.append(hp.submit(Cp, xh_, yh_, rc_))
-            if len(pending) == 2:
+            if len(pending) == LANES:
                 hp.wait(pending.pop(0))
         while pending:
             hp.wait(pending.pop(0))
 
-    e2e_steps = max(2, args.steps)
-    run_e2e(2)
+    e2e_steps = max(LANES, args.steps)
+    run_e2e(LANES)
     barrier()
     t0 = time.perf_counter()
     run_e2e(e2e_steps)
@@ -449,7 +450,7 @@ def run_b200(args):
             "config": bench_config(world),
             "e2e": {"value": round(world * B / e2e_s, 2), "unit": "instances/s", "h2d_bytes_per_step": int(Ch.nbytes),
                     "d2h_bytes_per_step": int(B * n * 8 * 2 + rch.nbytes + 4), "steps": e2e_steps,
-                    "api": "b200lap_pipeline_batch_submit/_wait, two batches in flight",
+                    "api": f"b200lap_pipeline_batch_submit/_wait, {LANES} batches in flight",
                     "one_batch_at_a_time": {"value": round(world * B / e2e_sync_s, 2), "unit": "instances/s", "api": "b200lap_pipeline_batch"}},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),

@@ -256,13 +256,13 @@ class Context:
     def pipeline(self, model: "Model", C, eps: float = 1e-12, want_trace: bool = False):
         """features -> OneGNN -> min-trick -> seeded JV without leaving the device.
 
-        With ``set_overlap(True)`` consecutive calls alternate between the context's two lanes (two independent batches
-        in flight: a 64-instance solve occupies 64 of the 148 SMs); the returned tensors are then complete only after
+        With ``set_overlap(k)`` consecutive calls rotate through k of the context's lanes (k independent batches in
+        flight: one 64-instance solve occupies 64 of the 148 SMs); the returned tensors are then complete only after
         ``sync()`` -- or, for work on torch's current stream, after ``join()`` + ``wait_for_context()``."""
         torch = _torch()
         cur = torch.cuda.current_stream(self.device)
         overlap = getattr(self, "_overlap", False)
-        lanes = [self.lane_stream(0), self.lane_stream(1)] if overlap else [self.torch_stream()]
+        lanes = [self.lane_stream(k) for k in range(overlap)] if overlap else [self.torch_stream()]
         for st in lanes:
             if cur.cuda_stream != st.cuda_stream:
                 st.wait_stream(cur)                     # C (and the model) are complete before our kernels read them
@@ -288,13 +288,15 @@ class Context:
         torch = _torch()
         if getattr(self, "_lanes", None) is None:
             self._lanes = [torch.cuda.ExternalStream(int(self.lib.b200lap_ctx_lane_stream(self.handle, k) or 0), device=self.device)
-                           for k in (0, 1)]
+                           for k in range(4)]
         return self._lanes[lane]
 
-    def set_overlap(self, on: bool):
-        """Alternate whole-pipeline calls between the two lanes (see ``pipeline``)."""
-        self._overlap = bool(on)
-        self.set_option("overlap_steps", 1 if on else 0)
+    def set_overlap(self, lanes):
+        """Rotate whole-pipeline calls through `lanes` lanes (2..4; False/0/1 = off; see ``pipeline``)."""
+        lanes = 2 if lanes is True else int(lanes or 0)
+        lanes = 0 if lanes < 2 else min(lanes, 4)
+        self._overlap = lanes
+        self.set_option("overlap_steps", lanes)
 
     def join(self):
         """Lane 0's stream (``torch_stream()``) waits on the device for everything enqueued on lane 1."""
@@ -311,11 +313,13 @@ class HostPipeline:
         hp.wait(t)                                              # x, y, rc are complete
     """
 
-    def __init__(self, state_dict: Mapping, topk: int = 16):
+    def __init__(self, state_dict: Mapping, topk: int = 16, lanes: int = 2):
         self.lib = _lib.load()
         self.ctx = self.lib.b200lap_default_ctx()
         if not self.ctx:
             raise B200LapError("no CUDA device is visible: b200lap has no CPU path")
+        self.lanes = max(2, min(int(lanes), 4))
+        check(self.lib.b200lap_ctx_set_option(self.ctx, b"overlap_steps", self.lanes), "b200lap_ctx_set_option", self.lib)
         blob, in_dim, hidden, layers = pack_state_dict(state_dict)
         h = ctypes.c_void_p()
         check(self.lib.b200lap_model_create(self.ctx, blob.ctypes.data, blob.size, in_dim, hidden, layers, int(topk), ctypes.byref(h)),

@@ -80,16 +80,22 @@ struct b200lap_ctx {
     // lanes when `overlap_steps` is on, so two batches are in flight and the SMs a 64-instance batch leaves idle
     // (one CTA per instance) work on the other batch.  `stream` / `blocks` always name the ACTIVE lane; outside a
     // call that is lane 0.
-    cudaStream_t stream2 = nullptr;
-    std::vector<WsBlock> blocks2;
-    cudaEvent_t lane_ev = nullptr;
+    static constexpr int kMaxLanes = 4;
+    struct LaneStore { cudaStream_t stream = nullptr; std::vector<WsBlock> blocks; cudaEvent_t ev = nullptr; };
+    LaneStore parked[kMaxLanes];  // lanes 1..: their stream/blocks while inactive; slot a holds LANE 0's while lane a is active
     int active_lane = 0;
-    int overlap_steps = 0;       // option: b200lap_dev_pipeline / pipeline_batch_submit alternate lanes
+    int overlap_steps = 0;       // option: number of lanes independent whole-pipeline calls rotate through (0/1 = off, up to 4)
     long long lane_calls = 0;
+    int lanes() const { return overlap_steps < 2 ? 1 : (overlap_steps > kMaxLanes ? kMaxLanes : overlap_steps); }
     void use_lane(int l) {
-        if (l != active_lane) { std::swap(stream, stream2); std::swap(blocks, blocks2); active_lane = l; }
+        if (l == active_lane) return;
+        if (active_lane != 0) { std::swap(stream, parked[active_lane].stream); std::swap(blocks, parked[active_lane].blocks); active_lane = 0; }
+        if (l != 0) { std::swap(stream, parked[l].stream); std::swap(blocks, parked[l].blocks); active_lane = l; }
     }
-    cudaStream_t lane_stream(int l) const { return l == active_lane ? stream : stream2; }
+    cudaStream_t lane_stream(int l) const {
+        if (l == active_lane) return stream;
+        return l == 0 ? parked[active_lane].stream : parked[l].stream;
+    }
 
     void ws_reset() {
         for (auto& b : blocks) b.off = 0;
@@ -438,11 +444,13 @@ int b200lap_ctx_create(int device, void* stream, b200lap_ctx** out) {
         if (e != cudaSuccess) { delete c; return fail(B200LAP_ERR_CUDA, "cudaStreamCreate failed"); }
         c->own_stream = true;
     }
-    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->lane_ev, cudaEventDisableTiming) != cudaSuccess) {
-        (void)cudaGetLastError();
-        delete c;
-        return fail(B200LAP_ERR_CUDA, "cudaStreamCreate failed (second lane)");
+    for (int l = 1; l < b200lap_ctx::kMaxLanes; ++l) {
+        if (cudaStreamCreateWithFlags(&c->parked[l].stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->parked[l].ev, cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            delete c;
+            return fail(B200LAP_ERR_CUDA, "cudaStreamCreate failed (lanes)");
+        }
     }
     *out = c;
     return 0;
@@ -453,31 +461,36 @@ void b200lap_ctx_destroy(b200lap_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ctx->use_lane(0);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     for (auto& b : ctx->blocks) cudaFree(b.p);
-    for (auto& b : ctx->blocks2) cudaFree(b.p);
+    for (int l = 1; l < b200lap_ctx::kMaxLanes; ++l) {
+        if (ctx->parked[l].stream) cudaStreamSynchronize(ctx->parked[l].stream);
+        for (auto& b : ctx->parked[l].blocks) cudaFree(b.p);
+        if (ctx->parked[l].ev) cudaEventDestroy(ctx->parked[l].ev);
+        if (ctx->parked[l].stream) cudaStreamDestroy(ctx->parked[l].stream);
+    }
     for (auto& kv : ctx->posenc) cudaFree(kv.second);
-    if (ctx->lane_ev) cudaEventDestroy(ctx->lane_ev);
-    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 void* b200lap_ctx_stream(b200lap_ctx* ctx) { return ctx ? (void*)ctx->lane_stream(0) : nullptr; }
-void* b200lap_ctx_lane_stream(b200lap_ctx* ctx, int lane) { return ctx ? (void*)ctx->lane_stream(lane ? 1 : 0) : nullptr; }
+void* b200lap_ctx_lane_stream(b200lap_ctx* ctx, int lane) {
+    return (ctx && lane >= 0 && lane < b200lap_ctx::kMaxLanes) ? (void*)ctx->lane_stream(lane) : nullptr;
+}
 
 int b200lap_ctx_sync(b200lap_ctx* ctx) {
     if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
-    CK(cudaStreamSynchronize(ctx->lane_stream(0)));
-    CK(cudaStreamSynchronize(ctx->lane_stream(1)));
+    for (int l = 0; l < b200lap_ctx::kMaxLanes; ++l) CK(cudaStreamSynchronize(ctx->lane_stream(l)));
     return 0;
 }
 
-/* lane 0's stream waits (on the device) for everything enqueued on lane 1 so far */
+/* lane 0's stream waits (on the device) for everything enqueued on the other lanes so far */
 int b200lap_ctx_join(b200lap_ctx* ctx) {
     if (!ctx) return fail(B200LAP_ERR_ARG, "ctx is null");
-    CK(cudaEventRecord(ctx->lane_ev, ctx->lane_stream(1)));
-    CK(cudaStreamWaitEvent(ctx->lane_stream(0), ctx->lane_ev, 0));
+    for (int l = 1; l < b200lap_ctx::kMaxLanes; ++l) {
+        CK(cudaEventRecord(ctx->parked[l].ev, ctx->lane_stream(l)));
+        CK(cudaStreamWaitEvent(ctx->lane_stream(0), ctx->parked[l].ev, 0));
+    }
     return 0;
 }
 
