@@ -12,9 +12,11 @@ data-path collective); the timed region is bracketed by barrier + synchronize, t
   value      device-resident throughput (C already in HBM as binary32), CUDA events on the context stream
   e2e        the same step through the host-buffer C ABI (b200lap_pipeline_batch): pinned host float64 in,
              host int64 assignments out, host<->device copies inside the timed region
-  roofline   dominant dense-pass kernel (the row-feature sweep: k_row_features_warp at n = 2048, k_row_features_smem above) at algorithmic bytes = one read of C = 4 n^2 B per
-             instance, timed live with CUDA events; `traffic` = DRAM bytes of one launch from the committed ncu
-             capture (profiles/r01_ncu_row_features_smem.json); per-kernel table in `dense_pass`
+  roofline   dominant dense-pass kernel (the row-feature sweep: k_row_features_group + the redo pass of
+             k_row_features_smem) at algorithmic bytes = one read of C = 4 n^2 B per instance, timed live with CUDA
+             events; `traffic` = DRAM bytes of one launch from the committed ncu capture of the same kernel
+             (profiles/r02_ncu_row_features_group.json); per-kernel tables in `dense_pass_*`
+  other_configs   BASELINE configs 1, 3, 4, 5 (reduced batch for 5), timed in the same run on rank 0 at N=1
   cpu_baseline   the oracle's CPU pipeline (NumPy features, NumPy OneGNN, reference-compiled lapjv_seeded when
              oracle/_ref travelled, else the C port) on a bounded sample, on this box's host cores; plus SciPy.
 
@@ -52,9 +54,10 @@ METRIC = "LAP instances/s end-to-end (features -> OneGNN -> min-trick -> lapjv_s
 
 
 def load_traffic(workload: str):
-    """DRAM read+write bytes of one k_row_features_smem launch on `workload`, from the committed ncu --set full capture."""
+    """DRAM read+write bytes of one k_row_features_group launch on `workload`, from the committed ncu --set full capture
+    of the kernel this bench times (profiles/r02_ncu_row_features_group.json)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_row_features_smem.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_row_features_group.json")) as f:
             rec = json.load(f)[workload]
         return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"])
     except Exception:  # noqa: BLE001
@@ -73,7 +76,7 @@ def bench_config(world: int) -> dict:
     """The `config` object of both arms (the driver compares them key by key)."""
     return {"workload": f"{BATCH} mixed-family n={N_INST} instances per GPU (BASELINE configs[1], mid2048), random-init OneGNN h192/L4/k16",
             "families": list(FAMILIES), "storage": "binary32 C on the device (exact), binary64 solver arithmetic; binary64 on the host",
-            "l2": "inputs (1.07 GB/step) larger than L2", "parallelism": f"instance-sharded x{world}", "steps_in_flight": int(os.environ.get("B200LAP_LANES", "2"))}
+            "l2": "inputs (1.07 GB/step) larger than L2", "parallelism": f"instance-sharded x{world}", "steps_in_flight": int(os.environ.get("B200LAP_LANES", "4"))}
 
 
 def named_state_dict():
@@ -256,6 +259,109 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+# ---- the other BASELINE configs (rank 0, N=1): parity-test shapes, timed in the same run -------------------------
+def other_configs(ctx, model, args):
+    """configs[0] single uniform n=512 (host API latency, with the reference's CPU pipeline beside it), configs[2]
+    32 x metric n=4096 (fallback path), configs[3] single uniform n=16384 end to end, configs[4] n=8192 mixed, solver
+    only, oracle duals + N(0, sigma) noise (scripts/main_benchmark.py:45, solvers/dual_computation.py:77-115) at
+    --batch5 instances."""
+    import torch
+    import b200lap
+    import lap
+    from solvers import generators as gen
+    stream = ctx.torch_stream()
+    out = {}
+
+    def ev_time(fn, reps=3, warm=1):
+        for _ in range(warm):
+            fn()
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            r = fn()
+        e1.record(stream)
+        ctx.sync()
+        return e0.elapsed_time(e1) / reps, r
+
+    def counters(tr):
+        tr = tr.cpu().numpy()
+        return {"took_fallback": int(tr[:, 3].sum()), "aug_paths": int(tr[:, 7].sum()), "relax_cols": int(tr[:, 9].sum()),
+                "arr_iters": int(tr[:, 6].sum()), "proj_triggers": int(tr[:, 0].sum())}
+
+    try:
+        # config 1: the reference-facing call, lap.lapjv_seeded(C, u, v) after GNNPredictor.predict(C), host buffers
+        C = gen.make_instance("uniform", 512, 42)
+        pred = b200lap.GNNPredictor(named_state_dict(), device=ctx.device, ctx=ctx)
+
+        def host():
+            u, v = pred.predict(C)
+            return lap.lapjv_seeded(C, u, v)
+        host()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            host()
+        ms = (time.perf_counter() - t0) / 10 * 1e3
+        dms, r = ev_time(lambda: ctx.pipeline(model, pred.to_device(C), want_trace=True), reps=10)
+        out["config1_uniform_512"] = {"host_api_ms": round(ms, 3), "device_resident_ms": round(dms, 3), "counters": counters(r[5])}
+    except Exception as exc:  # noqa: BLE001
+        out["config1_uniform_512"] = {"error": repr(exc)}
+    try:
+        n3, B3 = 4096, 32
+        Cd = torch.empty((B3, n3, n3), dtype=torch.float32, device="cuda")
+        for k in range(B3):
+            Cd[k] = torch.from_numpy(gen.make_instance("metric", n3, 42 + k).astype(np.float32)).cuda()
+        ms, r = ev_time(lambda: ctx.pipeline(model, Cd, want_trace=True))
+        pms, _ = ev_time(lambda: ctx.predict_duals(model, Cd))
+        assert (r[2] == 0).all()
+        out["config3_metric_4096_x32"] = {"pipeline_ms": round(ms, 3), "predict_ms": round(pms, 3), "inst_per_s": round(B3 / ms * 1e3, 1),
+                                          "counters": counters(r[5])}
+        del Cd
+    except Exception as exc:  # noqa: BLE001
+        out["config3_metric_4096_x32"] = {"error": repr(exc)}
+    try:
+        n4 = 16384
+        Cd = torch.rand((n4, n4), generator=torch.Generator(device="cuda").manual_seed(42), device="cuda", dtype=torch.float32)
+        pms, duals = ev_time(lambda: ctx.predict_duals(model, Cd), reps=5)
+        t0 = time.perf_counter()
+        x, y, rc, tr = ctx.solve_seeded(Cd, duals[0], duals[1], want_trace=True)
+        ctx.sync()
+        sms = (time.perf_counter() - t0) * 1e3
+        assert int(rc[0]) == 0 and bool((torch.sort(x[0].long()).values == torch.arange(n4, device="cuda")).all())
+        out["config4_uniform_16384"] = {"predict_ms": round(pms, 3), "solve_ms": round(sms, 1), "inst_per_s": round(1e3 / (pms + sms), 4),
+                                        "counters": counters(tr)}
+        del Cd
+    except Exception as exc:  # noqa: BLE001
+        out["config4_uniform_16384"] = {"error": repr(exc)}
+    try:
+        n5, B5 = 8192, int(args.batch5)
+        Cd = torch.empty((B5, n5, n5), dtype=torch.float32, device="cuda")
+        for k in range(B5):
+            Cd[k] = torch.from_numpy(gen.make_instance(FAMILIES[k % 4], n5, 42 + k).astype(np.float32)).cuda()
+        t0 = time.perf_counter()
+        xc, yc, rcc, vfin = ctx.solve_cold(Cd, want_v=True)
+        ctx.sync()
+        cold_ms = (time.perf_counter() - t0) * 1e3
+        u_opt = (Cd.double() - vfin[:, None, :]).min(dim=2).values
+        rec = {"batch": B5, "oracle_duals_by_cold_solve_ms": round(cold_ms, 1)}
+        for sigma in (0.0, 1e-3, 1e-2):
+            gn = torch.Generator(device="cuda").manual_seed(42)
+            u = u_opt + sigma * torch.randn(u_opt.shape, generator=gn, device="cuda", dtype=torch.float64)
+            v = vfin + sigma * torch.randn(u_opt.shape, generator=gn, device="cuda", dtype=torch.float64)
+            t0 = time.perf_counter()
+            x, y, rc, tr = ctx.solve_seeded(Cd, u, v, want_trace=True)
+            ctx.sync()
+            ms = (time.perf_counter() - t0) * 1e3
+            assert (rc == 0).all()
+            rec[f"sigma_{sigma:g}"] = {"solve_ms": round(ms, 1), "inst_per_s": round(B5 / ms * 1e3, 3), "counters": counters(tr)}
+        out["config5_mixed_8192_oracle_duals_plus_noise"] = rec
+        del Cd
+    except Exception as exc:  # noqa: BLE001
+        out["config5_mixed_8192_oracle_duals_plus_noise"] = {"error": repr(exc)}
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---- the B200 arm ----------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -286,12 +392,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # -- device-resident throughput: two batches in flight (the context's two lanes alternate), so the SMs one
-    #    64-instance solve leaves idle (one CTA per instance, 148 SMs) work on the neighbouring step
+    # -- device-resident throughput: B200LAP_LANES batches in flight (the context's lanes rotate), so the SMs one
+    #    64-instance solve leaves idle (one CTA per instance, 148 SMs) work on the neighbouring steps
     def step_resident():
         return ctx.pipeline(model, Cd)
 
-    LANES = int(os.environ.get("B200LAP_LANES", "2"))
+    LANES = int(os.environ.get("B200LAP_LANES", "4"))
     ctx.set_overlap(LANES)
     for _ in range(args.warmup):
         out = step_resident()
@@ -354,8 +460,21 @@ def run_b200(args):
                      ("predict_duals", lambda: ctx.predict_duals(model, Cd))):
         ms = timed(fn, reps)
         dense[name] = {"ms": round(ms, 4), "GBps_one_read_of_C": round(bytes_one_read / (ms * 1e-3) / 1e9, 1)}
+    ctx.row_features(Cd, topk=16)
+    redo_rows = ctx.feature_redo_rows()
     solve_ms = timed(lambda: ctx.solve_seeded(Cd, u64, v64), max(2, args.steps // 2))
     dense["solve_seeded"] = {"ms": round(solve_ms, 3)}
+    # what the random-init seeds make the solver do (the headline depends on it), per family
+    counters = None
+    try:
+        tr = ctx.solve_seeded(Cd, u64, v64, want_trace=True)[3].cpu().numpy()
+        counters = {}
+        for f in FAMILIES:
+            rows = tr[[k for k in range(B) if fams[k] == f]]
+            counters[f] = {"took_fallback_rate": round(float(rows[:, 3].mean()), 3), "mean_aug_paths": round(float(rows[:, 7].mean()), 1),
+                           "mean_proj_triggers": round(float(rows[:, 0].mean()), 1), "mean_tight_edges": round(float(rows[:, 1].mean()), 1)}
+    except Exception as exc:  # noqa: BLE001
+        counters = {"error": repr(exc)}
 
     # -- the n = 16384 dense pass (config 4: 1 GiB binary32 C), the size the HBM target is quoted on
     big = None
@@ -420,6 +539,9 @@ def run_b200(args):
     assert np.array_equal(out[0].cpu().numpy().astype(np.int64), xh.numpy()), "host and resident paths disagree"
     assert np.array_equal(hbuf[1][0].numpy(), xh.numpy()) and np.array_equal(hbuf[1][1].numpy(), yh.numpy()), "asynchronous host path disagrees"
 
+    others = None
+    if rank == 0 and world == 1 and not args.skip_configs:
+        others = other_configs(ctx, model, args)
     if rank == 0:
         peak, which = load_peaks()
         fk = dense["row_features"]
@@ -454,11 +576,17 @@ def run_b200(args):
                     "one_batch_at_a_time": {"value": round(world * B / e2e_sync_s, 2), "unit": "instances/s", "api": "b200lap_pipeline_batch"}},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"bound": "hbm", "kernel": "row-feature sweep: k_row_features_warp + the redo pass of k_row_features_smem (21-D features + top-16, one read of C)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "row-feature sweep: k_row_features_group<1,64> + the redo pass of k_row_features_smem (21-D features + top-16, one read of C)", "achieved": achieved,
                          "peak": peak, "peak_source": which, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "algorithmic_bytes_per_launch": bytes_one_read, "traffic": load_traffic("n2048_b64")},
+                         "algorithmic_bytes_per_launch": bytes_one_read, "traffic": load_traffic("n2048_b64"),
+                         "rows_handed_to_fallback_kernel": redo_rows,
+                         "n16384": None if not big or "row_features" not in big else
+                         {"achieved": big["row_features"]["GBps_one_read_of_C"], "frac": round(big["row_features"]["GBps_one_read_of_C"] / peak, 4),
+                          "dense_pass_frac": round(big["predict_duals"]["GBps_one_read_of_C"] / peak, 4), "traffic": load_traffic("n16384_b1")}},
             "dense_pass_n2048_b64": dense,
             "dense_pass_n16384": big,
+            "solver_counters": counters,
+            "other_configs": others,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
@@ -506,6 +634,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
     ap.add_argument("--skip-big", action="store_true", help="omit the n=16384 dense-pass table")
+    ap.add_argument("--skip-configs", action="store_true", help="omit BASELINE configs 1, 3, 4, 5 (`other_configs`)")
+    ap.add_argument("--batch5", type=int, default=8, help="instances of config 5 (n=8192, oracle duals + noise) on this GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -41,6 +41,7 @@ SIGNATURES = {
     "b200lap_ctx_sync": (ctypes.c_int, [vp]),
     "b200lap_ctx_set_option": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_longlong]),
     "b200lap_ctx_launch_count": (ctypes.c_longlong, [vp]),
+    "b200lap_ctx_feature_redo_rows": (ctypes.c_longlong, [vp]),
     "b200lap_last_error": (ctypes.c_char_p, []),
     "b200lap_device_count": (ctypes.c_int, []),
     "b200lap_dev_narrow": (ctypes.c_int, [vp, vp, ctypes.c_longlong, vp, vp]),

@@ -118,6 +118,10 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.b200lap_ctx_launch_count(self.handle))
 
+    def feature_redo_rows(self):
+        """Rows of the last row-feature call that the fast kernel handed to the exact fall-back (diagnostic)."""
+        return int(self.lib.b200lap_ctx_feature_redo_rows(self.handle))
+
     # ---- device-pointer entry points (arguments are torch CUDA tensors on this context's device) ----
     def _empty(self, shape, dtype):
         torch = _torch()
@@ -288,13 +292,13 @@ class Context:
         torch = _torch()
         if getattr(self, "_lanes", None) is None:
             self._lanes = [torch.cuda.ExternalStream(int(self.lib.b200lap_ctx_lane_stream(self.handle, k) or 0), device=self.device)
-                           for k in range(4)]
+                           for k in range(8)]
         return self._lanes[lane]
 
     def set_overlap(self, lanes):
-        """Rotate whole-pipeline calls through `lanes` lanes (2..4; False/0/1 = off; see ``pipeline``)."""
+        """Rotate whole-pipeline calls through `lanes` lanes (2..8; False/0/1 = off; see ``pipeline``)."""
         lanes = 2 if lanes is True else int(lanes or 0)
-        lanes = 0 if lanes < 2 else min(lanes, 4)
+        lanes = 0 if lanes < 2 else min(lanes, 8)
         self._overlap = lanes
         self.set_option("overlap_steps", lanes)
 
@@ -318,7 +322,7 @@ class HostPipeline:
         self.ctx = self.lib.b200lap_default_ctx()
         if not self.ctx:
             raise B200LapError("no CUDA device is visible: b200lap has no CPU path")
-        self.lanes = max(2, min(int(lanes), 4))
+        self.lanes = max(2, min(int(lanes), 8))
         check(self.lib.b200lap_ctx_set_option(self.ctx, b"overlap_steps", self.lanes), "b200lap_ctx_set_option", self.lib)
         blob, in_dim, hidden, layers = pack_state_dict(state_dict)
         h = ctypes.c_void_p()

@@ -3,6 +3,8 @@
 // Every entry point enqueues hand-written sm_100a kernels on the context's stream; nothing here
 // computes on the host.  Built by nvcc only (build.py); the same translation unit also compiles
 // against tests/emul/cuda_emul.h for the CPU-side logic tests (test infrastructure, not shipped).
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -18,6 +20,7 @@
 #include "features.cuh"
 #include "features_smem.cuh"
 #include "features_warp.cuh"
+#include "features_group.cuh"
 #include "mlp.cuh"
 #include "mlp_tc.cuh"
 #include "../../include/b200lap.h"
@@ -73,6 +76,9 @@ struct b200lap_ctx {
     int feat_nbuf = 0;
     int feat_nsamp = 0;
     int feat_ctas = 0;
+    const int* feat_redo_count = nullptr;   // device counter of the last row-feature call (rows the fast kernel handed to the fall-back)
+    cudaStream_t feat_redo_stream = nullptr;
+    int feat_group = 0;          // option: warps per row of the group kernel (0 = auto: n / 2048, 1..8 forces; needs n = 32 * G * {16, 32, 64, 128})
     int sm_count = 148;
     std::map<int, float*> posenc;   // positional-encoding tables [n][8], one per n ever used (never freed before the ctx)
     std::mutex mu;
@@ -80,11 +86,11 @@ struct b200lap_ctx {
     // lanes when `overlap_steps` is on, so two batches are in flight and the SMs a 64-instance batch leaves idle
     // (one CTA per instance) work on the other batch.  `stream` / `blocks` always name the ACTIVE lane; outside a
     // call that is lane 0.
-    static constexpr int kMaxLanes = 4;
+    static constexpr int kMaxLanes = 8;
     struct LaneStore { cudaStream_t stream = nullptr; std::vector<WsBlock> blocks; cudaEvent_t ev = nullptr; };
     LaneStore parked[kMaxLanes];  // lanes 1..: their stream/blocks while inactive; slot a holds LANE 0's while lane a is active
     int active_lane = 0;
-    int overlap_steps = 0;       // option: number of lanes independent whole-pipeline calls rotate through (0/1 = off, up to 4)
+    int overlap_steps = 0;       // option: number of lanes independent whole-pipeline calls rotate through (0/1 = off, up to 8)
     long long lane_calls = 0;
     int lanes() const { return overlap_steps < 2 ? 1 : (overlap_steps > kMaxLanes ? kMaxLanes : overlap_steps); }
     void use_lane(int l) {
@@ -496,6 +502,15 @@ int b200lap_ctx_join(b200lap_ctx* ctx) {
 
 long long b200lap_ctx_launch_count(b200lap_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+long long b200lap_ctx_feature_redo_rows(b200lap_ctx* ctx) {
+    if (!ctx || !ctx->feat_redo_count) return 0;
+    int c[4] = {0, 0, 0, 0};
+    if (cudaStreamSynchronize(ctx->feat_redo_stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(c, ctx->feat_redo_count, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (getenv("B200LAP_FEAT_DEBUG")) fprintf(stderr, "[b200lap] feature redo rows %d: list overflow / candidates %d, bracket miss %d, tie-heavy target bin %d\n", c[0], c[1], c[2], c[3]);
+    return c[0];
+}
+
 int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value) {
     if (!ctx || !key) return fail(B200LAP_ERR_ARG, "null argument");
     const std::string k(key);
@@ -516,6 +531,7 @@ int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value) {
     else if (k == "feat_nbuf") ctx->feat_nbuf = (int)value;
     else if (k == "feat_nsamp") ctx->feat_nsamp = (int)value;
     else if (k == "feat_ctas") ctx->feat_ctas = (int)value;
+    else if (k == "feat_group") ctx->feat_group = (int)value;
     else return fail(B200LAP_ERR_ARG, "unknown option " + k);
     return 0;
 }

@@ -74,6 +74,9 @@ int b200lap_ctx_join(b200lap_ctx* ctx);
  * floating-point summation orders (features stay inside the stated 1e-4 tolerance). */
 int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value);
 long long b200lap_ctx_launch_count(b200lap_ctx* ctx); /* kernels launched so far on this context */
+/* rows of the LAST row-feature call on this context that the fast kernel handed to the exact fall-back kernel
+ * (diagnostic; synchronises the stream; valid until the next call that resets the context workspace) */
+long long b200lap_ctx_feature_redo_rows(b200lap_ctx* ctx);
 const char* b200lap_last_error(void);
 int b200lap_device_count(void);
 

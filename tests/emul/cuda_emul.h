@@ -77,6 +77,8 @@ struct Block {
     int cur = -1;
     int bar_arrived = 0;
     int bar_gen = 0;
+    int named_arrived[16] = {0};
+    int named_gen[16] = {0};
     int nthreads = 0;
     const std::function<void()>* body = nullptr;
 };
@@ -97,6 +99,14 @@ inline void block_barrier() {
     int g = b->bar_gen;
     if (++b->bar_arrived == b->nthreads) { b->bar_arrived = 0; b->bar_gen++; return; }
     while (b->bar_gen == g) yield();
+}
+
+// bar.sync id, count: the first `count` threads to arrive at barrier `id` release each other
+inline void named_barrier(int id, int count) {
+    Block* b = g_block();
+    int g = b->named_gen[id];
+    if (++b->named_arrived[id] == count) { b->named_arrived[id] = 0; b->named_gen[id]++; return; }
+    while (b->named_gen[id] == g) yield();
 }
 
 inline void warp_barrier() {

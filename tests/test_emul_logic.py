@@ -287,6 +287,55 @@ def test_row_features_warp_kernel(emu):
     assert np.array_equal(topv, np.sort(Cf, axis=1)[:, :16])
 
 
+@pytest.mark.parametrize("n,group", [(512, 0), (1024, 2), (2048, 4)])
+def test_row_features_group_kernel(emu, n, group):
+    """The group kernel (features_group.cuh: G warps per row, sorted-sample brackets, lane-private byte histograms)
+    with its redo hand-over to the CTA kernel, for one, two and four warps per row: uniform, 1e6-fill (count-only
+    tie variant), clamped-at-zero rows, metric-style isolated minima, ties around the median, sorted / periodic rows."""
+    from oracle import features_np
+    lib, ctx = emu
+    rng = np.random.default_rng(n)
+    rows = 96 if n > 512 else n                                  # the emulator is slow: a rectangular slice of rows
+    C = rng.uniform(0, 1, (n, n))
+    j = np.arange(n)
+    fill = rng.uniform(size=(16, n)) > 0.3
+    C[16:32][fill] = 1e6                                         # sparse family rows
+    C[32:48] = np.clip(C[32:48] - 0.4 + 0.1 * rng.normal(size=(16, n)), 0, None)   # clustered-style zeros
+    pts = rng.uniform(0, 100, (n, 2))
+    C[48:64] = np.sqrt(((pts[48:64, None, :] - pts[None, :, :]) ** 2).sum(-1))      # metric rows: min 0, exp sum ~ 2
+    C[0] = 3.25
+    C[1] = np.where(j < n // 2, 0.0, 1.0)
+    C[2] = j
+    C[3] = j[::-1] * 0.5
+    C[4] = j % 4
+    C[5] = 1000.0; C[5, 17] = 0.0
+    C[6] = rng.integers(0, 3, n)
+    C[7] = np.where(j % 2 == 0, 5.0, rng.uniform(4.9, 5.1, n))
+    C[8] = rng.normal(50, 10, n)
+    C[9] = np.exp(rng.normal(0, 4, n))
+    C[10, :40] = 0.0
+    C = C.astype(np.float32).astype(np.float64)
+    ref = features_np.row_features(C)[:rows]
+    Cf = np.ascontiguousarray(C, dtype=np.float32)
+    feat = np.zeros((n, 21), np.float32)
+    topv = np.zeros((n, 16), np.float32)
+    _opt(lib, ctx, "feat_group", group)
+    try:
+        if rows < n:
+            # only the first `rows` rows matter: park the rest on the constant row so the emulator skips their lists
+            Cf[rows:] = 3.25
+            C2 = Cf.astype(np.float64)
+            ref = features_np.row_features(C2)[:rows]
+        assert lib.b200lap_dev_row_features(ctx, Cf.ctypes.data, 0, 1, n, 16, None, feat.ctypes.data, topv.ctypes.data) == 0
+        redo = lib.b200lap_ctx_feature_redo_rows(ctx)
+    finally:
+        _opt(lib, ctx, "feat_group", 0)
+    print("rows handed to the fall-back kernel:", redo)
+    assert 0 <= redo <= 16, redo          # the adversarial rows may give up; the family rows must not
+    feature_close(feat[:rows], ref, rtol=1e-4)
+    assert np.array_equal(topv[:rows], np.sort(Cf, axis=1)[:rows, :16])
+
+
 def test_advanced_dual_sweeps(emu):
     """solvers/advanced_dual.py:14-63 through the C ABI (project_feasible, reduce_costs / min reduced cost) against the
     NumPy statements, bit for bit, binary32- and binary64-stored matrices."""
