@@ -76,7 +76,7 @@ def bench_config(world: int) -> dict:
     """The `config` object of both arms (the driver compares them key by key)."""
     return {"workload": f"{BATCH} mixed-family n={N_INST} instances per GPU (BASELINE configs[1], mid2048), random-init OneGNN h192/L4/k16",
             "families": list(FAMILIES), "storage": "binary32 C on the device (exact), binary64 solver arithmetic; binary64 on the host",
-            "l2": "inputs (1.07 GB/step) larger than L2", "parallelism": f"instance-sharded x{world}", "steps_in_flight": int(os.environ.get("B200LAP_LANES", "4"))}
+            "l2": "inputs (1.07 GB/step) larger than L2", "parallelism": f"instance-sharded x{world}", "steps_in_flight": int(os.environ.get("B200LAP_LANES", "8"))}
 
 
 def named_state_dict():
@@ -397,7 +397,7 @@ def run_b200(args):
     def step_resident():
         return ctx.pipeline(model, Cd)
 
-    LANES = int(os.environ.get("B200LAP_LANES", "4"))
+    LANES = int(os.environ.get("B200LAP_LANES", "8"))
     ctx.set_overlap(LANES)
     for _ in range(args.warmup):
         out = step_resident()

@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200lap_pipeline_batch": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp, vp, vp, vp, vp]),
     "b200lap_dev_project_feasible": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_double, vp]),
     "b200lap_dev_reduced_costs": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]),
+    "b200lap_dev_bf_duals": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.POINTER(ctypes.c_int)]),
     "b200lap_project_feasible": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_double, vp]),
     "b200lap_reduce_costs": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp]),
     "b200lap_ctx_lane_stream": (vp, [vp, ctypes.c_int]),

@@ -241,6 +241,28 @@ class Context:
         return tuple(out)
 
     @_ordered
+    def bf_duals(self, C, x):
+        """Column potentials of solvers/dual_computation.py:32-47 (Bellman-Ford over the difference constraints of an
+        optimal matching x: row -> column) for every instance of the batch -> (v f64[B,n], rounds)."""
+        import ctypes
+        torch = _torch()
+        C, f64, B, n = self._matrix_args(C)
+        x = x.to(torch.int32).contiguous().view(B, n)
+        v = self._empty((B, n), torch.float64)
+        rounds = ctypes.c_int(0)
+        check(self.lib.b200lap_dev_bf_duals(self.handle, ptr(C), f64, B, n, ptr(x), ptr(v), ctypes.byref(rounds)), "b200lap_dev_bf_duals", self.lib)
+        return v, int(rounds.value)
+
+    @_ordered
+    def row_features_torch(self, C, topk: int = 0):
+        """compute_row_features_torch's definitions (gnn/features.py:246-351) on a float32 device batch -> feat [B,n,21]."""
+        self.set_option("feat_torch_mode", 1)
+        try:
+            return self.row_features(C, topk=topk)[0]
+        finally:
+            self.set_option("feat_torch_mode", 0)
+
+    @_ordered
     def front_end(self, C, u, v, eps: float = 1e-12):
         """The solver's front-end sweep alone -> (u_tight f64[B,n], tight_cnt i32[B,n], any_violation bool[B],
         infeasible bool[B], total_tight int64[B])."""

@@ -78,6 +78,7 @@ struct b200lap_ctx {
     int feat_ctas = 0;
     const int* feat_redo_count = nullptr;   // device counter of the last row-feature call (rows the fast kernel handed to the fall-back)
     cudaStream_t feat_redo_stream = nullptr;
+    int feat_torch_mode = 0;     // option: 1 = the definitions of compute_row_features_torch (gnn/features.py:246-351)
     int feat_group = 0;          // option: warps per row of the group kernel (0 = auto: n / 2048, 1..8 forces; needs n = 32 * G * {16, 32, 64, 128})
     int sm_count = 148;
     std::map<int, float*> posenc;   // positional-encoding tables [n][8], one per n ever used (never freed before the ctx)
@@ -532,6 +533,7 @@ int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value) {
     else if (k == "feat_nsamp") ctx->feat_nsamp = (int)value;
     else if (k == "feat_ctas") ctx->feat_ctas = (int)value;
     else if (k == "feat_group") ctx->feat_group = (int)value;
+    else if (k == "feat_torch_mode") ctx->feat_torch_mode = (int)value;
     else return fail(B200LAP_ERR_ARG, "unknown option " + k);
     return 0;
 }
@@ -687,6 +689,54 @@ int run_project_feasible(b200lap_ctx* ctx, const CT* C, int n, double* u, double
     return 0;
 }
 
+
+// Oracle duals by difference constraints (solvers/dual_computation.py:13-47): Jacobi rounds of the Bellman-Ford
+// relaxation from v = 0 until no column potential moves (checked on the host every few rounds) or n - 1 rounds.
+template <typename CT>
+int run_bf_duals(b200lap_ctx* ctx, const CT* C, int batch, int n, const int* x, double* v, int* rounds_out)
+{
+    const long long st = (long long)n * n;
+    const int rps = strip_rows(n);
+    const int S = (n + rps - 1) / rps;
+    const size_t cnt = (size_t)batch * n;
+    TAKE(pval, double, (size_t)batch * S * n);
+    TAKE(cand, double, cnt);
+    TAKE(vx, double, cnt);
+    TAKE(cx, double, cnt);
+    TAKE(changed, int, 1);
+    CK(cudaMemsetAsync(v, 0, cnt * sizeof(double), ctx->stream));
+    const bool vec = vec_ok(C, st, n, n);
+    constexpr int V = natural_vec<CT>();
+    int rounds = 0, moved = 1;
+    const int max_rounds = n > 1 ? n - 1 : 1;
+    while (moved && rounds < max_rounds) {
+        CK(cudaMemsetAsync(changed, 0, sizeof(int), ctx->stream));
+        const int burst = rounds < 8 ? 4 : 16;                  // rounds between two looks at the flag
+        for (int q = 0; q < burst && rounds < max_rounds; ++q, ++rounds) {
+            B200LAP_LAUNCH(k_bf_gather, dim3((n + 255) / 256, batch), dim3(256), 0, ctx->stream, (const void*)C, (int)(sizeof(CT) == 8), st, n, n, x,
+                           (const double*)v, vx, cx);
+            if (vec) {
+                auto k = k_bf_relax_partial<CT, V>;
+                B200LAP_LAUNCH(k, dim3((n + kColThreads * V - 1) / (kColThreads * V), S, batch), dim3(kColThreads), 0, ctx->stream, C, st, n, n, rps,
+                               (const double*)vx, (const double*)cx, pval);
+            } else {
+                auto k = k_bf_relax_partial<CT, 1>;
+                B200LAP_LAUNCH(k, dim3((n + kColThreads - 1) / kColThreads, S, batch), dim3(kColThreads), 0, ctx->stream, C, st, n, n, rps,
+                               (const double*)vx, (const double*)cx, pval);
+            }
+            B200LAP_LAUNCH(k_min_trick_final, dim3((n + 255) / 256, batch), dim3(256), 0, ctx->stream, (const double*)pval, S, n, cand);
+            B200LAP_LAUNCH(k_bf_update, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, ctx->stream, v, (const double*)cand, (long long)cnt, changed);
+            ctx->launches += 4;
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&moved, changed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (rounds_out) *rounds_out = rounds;
+    // still moving after n - 1 rounds: the reference raises "Negative cycle ..." (the matching was not optimal)
+    return moved ? fail(B200LAP_ERR_ARG, "difference constraints did not converge in n - 1 rounds: the matching is not optimal (negative cycle)") : 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -708,6 +758,13 @@ int b200lap_dev_reduced_costs(b200lap_ctx* ctx, const void* C, int is_f64, int b
     const long long st = (long long)n * n;
     return is_f64 ? run_reduced_costs(ctx, (const double*)C, st, n, batch, n, u, v, out, min_host)
                   : run_reduced_costs(ctx, (const float*)C, st, n, batch, n, u, v, out, min_host);
+}
+
+int b200lap_dev_bf_duals(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const int* x, double* v, int* rounds) {
+    if (!ctx || !C || !x || !v) return fail(B200LAP_ERR_ARG, "null argument");
+    if (n <= 0 || batch <= 0) return fail(B200LAP_ERR_ARG, "empty problem");
+    ctx->ws_reset();
+    return is_f64 ? run_bf_duals(ctx, (const double*)C, batch, n, x, v, rounds) : run_bf_duals(ctx, (const float*)C, batch, n, x, v, rounds);
 }
 
 }  // extern "C"

@@ -111,4 +111,59 @@ __global__ void k_shift(double* __restrict__ out, long long count, double shift)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) out[i] = out[i] - shift;
 }
 
+
+// ---- oracle duals: the difference-constraint relaxation of solvers/dual_computation.py:13-47 --------------------
+// The reference builds, for every matched pair (row r_p, column p), the edges p -> j of weight w = C[r_p, j] - C[r_p, p]
+// and relaxes them Bellman-Ford style from v = 0 (`if v[b] > v[a] + w: v[b] = v[a] + w`) until nothing changes.  The
+// operator is monotone, so any relaxation order reaches the same (greatest) fixed point; evaluating every edge as the
+// reference does -- fl(v[a] + fl(c_ij - c_ip)) in binary64 -- makes that fixed point bit-identical.  Here one ROUND
+// relaxes all n^2 edges at once (Jacobi): a column-minimum sweep of C with two per-row scalars.
+__global__ void k_bf_gather(const void* __restrict__ C, int is_f64, long long inst_stride, int ld, int n, const int* __restrict__ x /* [B][n] row -> column */,
+                            const double* __restrict__ v /* [B][n] */, double* __restrict__ vx, double* __restrict__ cx)
+{
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = x[(size_t)b * n + i];
+    const size_t o = (size_t)b * inst_stride + (size_t)i * ld + p;
+    vx[(size_t)b * n + i] = v[(size_t)b * n + p];
+    cx[(size_t)b * n + i] = is_f64 ? reinterpret_cast<const double*>(C)[o] : (double)reinterpret_cast<const float*>(C)[o];
+}
+
+template <typename CT, int VEC>
+__global__ void __launch_bounds__(kColThreads) k_bf_relax_partial(
+    const CT* __restrict__ C, long long inst_stride, int ld, int n, int rows_per_strip,
+    const double* __restrict__ vx /* [B][n] v[x_i] */, const double* __restrict__ cx /* [B][n] c_{i, x_i} */, double* __restrict__ pval /* [B][S][n] */)
+{
+    const int b = blockIdx.z, strip = blockIdx.y, S = gridDim.y;
+    const int c0 = (blockIdx.x * kColThreads + threadIdx.x) * VEC;
+    if (c0 >= n) return;
+    const CT* base = C + (size_t)b * inst_stride;
+    const int r0 = strip * rows_per_strip;
+    const int r1 = min(n, r0 + rows_per_strip);
+    double best[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) best[e] = INFINITY;
+    for (int r = r0; r < r1; ++r) {
+        CT t[VEC];
+        VecLoad<CT, VEC>::ld(base + (size_t)r * ld + c0, t);
+        const double va = __ldg(vx + (size_t)b * n + r), ca = __ldg(cx + (size_t)b * n + r);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const double cand = va + ((double)t[e] - ca);
+            best[e] = cand < best[e] ? cand : best[e];
+        }
+    }
+    const size_t o = ((size_t)b * S + strip) * n + c0;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+        if (c0 + e < n) pval[o + e] = best[e];
+}
+
+// v = min(v, cand); *changed |= something moved
+__global__ void k_bf_update(double* __restrict__ v, const double* __restrict__ cand, long long count, int* __restrict__ changed)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) { const double a = v[i], c = cand[i]; if (a > c) { v[i] = c; *changed = 1; } }
+}
+
 }  // namespace b200lap

@@ -480,4 +480,25 @@ __global__ void __launch_bounds__(MAXT) k_row_features(
         write_row_features(feat + ((size_t)b * n + row) * kFeatDim, n, row, mn, mx, mean, ssq, mad, esum, ewsum, near, cb, S.sorted);
 }
 
+
+// ---- compute_row_features_torch (gnn/features.py:246-351) on top of the NumPy-definition features ---------------
+// The torch variant differs from compute_row_features in four places: row_std and k_std are unbiased (torch.std),
+// is_col_best counts only the FIRST row attaining each column minimum (argmin + bincount, :319-320) and the near-best
+// threshold is multiplied in binary32 (handled inside the feature kernels).
+__global__ void k_count_col_argmin(const int* __restrict__ colarg, int n, int* __restrict__ cnt /* [B][n], zeroed */)
+{
+    const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) atomicAdd(&cnt[(size_t)b * n + colarg[(size_t)b * n + j]], 1);
+}
+__global__ void k_feat_torch_fixup(float* __restrict__ feat, const int* __restrict__ cnt, int n, long long rows)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float* f = feat + r * kFeatDim;
+    const int k = n < 10 ? n : 10;
+    f[3] = n > 1 ? f[3] * sqrtf((float)n / (float)(n - 1)) : NAN;           // torch.std of one element is NaN
+    f[9] = k > 1 ? f[9] * sqrtf((float)k / (float)(k - 1)) : NAN;
+    f[12] = (float)cnt[r] / (float)n;
+}
+
 }  // namespace b200lap

@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
         redo = __any_sync(kFull, redo);
 
         // ---- rare extra pass over the on-chip segment: near-best count, exact variance, exp sum without the ones
-        const float near_thr = round_down_to<float>((double)mn * 1.1);
+        const float near_thr = near_threshold(mn, a.torch_mode);
         const double dmean = mean - (double)mn;
         const double var_z = (double)zz * inv_n_d - dmean * dmean;
         const bool need_near = !(near_thr < U);

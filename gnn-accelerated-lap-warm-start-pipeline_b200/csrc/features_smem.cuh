@@ -78,7 +78,13 @@ struct FeatSmemArgs {
     const int* rows_in_count;
     int* redo_list;            // warp kernel: rows handed to the CTA kernel's exact fall-backs
     int* redo_count;
+    int torch_mode = 0;        // near-best threshold as compute_row_features_torch evaluates it: fl32(row_min * 1.1f) (gnn/features.py:316)
 };
+
+// c <= mn * 1.1 in binary64 (NumPy definition)  <=>  c <= round_down(mn * 1.1); the torch definition multiplies in binary32
+__device__ __forceinline__ float near_threshold(float mn, int torch_mode) {
+    return torch_mode ? mn * 1.1f : round_down_to<float>((double)mn * 1.1);
+}
 
 // ---- order-preserving integer image of a binary32 value (for warp redux min / max) -----------------
 __device__ __forceinline__ unsigned f2ord(float f) {
@@ -726,7 +732,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_row_features_smem(FeatSmemArgs a
 
         // ---- rare extra passes (uniform conditions): near-best count when 1.1*min reaches the candidate bound,
         //      exact variance under cancellation, exp sum without the exact ones for an isolated minimum
-        const float near_thr = round_down_to<float>((double)mn * 1.1);   // c <= mn*1.1 in binary64 <=> c <= round_down(mn*1.1)
+        const float near_thr = near_threshold(mn, a.torch_mode);
         const float zz = sum_slots(F.psum[p][1]), es = sum_slots(F.psum[p][2]);
         const double dmean = mean - (double)mn;
         const double var_z = (double)zz * inv_n_d - dmean * dmean;

@@ -69,7 +69,8 @@ int b200lap_ctx_join(b200lap_ctx* ctx);
 /* Tuning / test options (0 = automatic unless stated): solver_threads, solver_cluster (CTAs per instance: 1 = single
  * CTA, 2/4/8 = thread-block cluster; auto = 8 from solver_cluster_min_n = 8192 on), force_global_state,
  * solver_smem_budget, front_rows_per_cta, mlp_impl (1 = FFMA instead of tcgen05), feat_impl (1 = register-resident
- * row-feature kernel), feat_threads, feat_nbuf, feat_nsamp, feat_ctas, feat_ept.  Unknown keys return
+ * row-feature kernel), feat_threads, feat_nbuf, feat_nsamp, feat_ctas, feat_ept, feat_group (warps per row of the group
+ * kernel), feat_torch_mode (1 = the definitions of compute_row_features_torch, gnn/features.py:246-351, binary32 input).  Unknown keys return
  * B200LAP_ERR_ARG.  No option changes an assignment or a selected order statistic; the feat_* launch shapes change
  * floating-point summation orders (features stay inside the stated 1e-4 tolerance). */
 int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value);
@@ -130,6 +131,13 @@ int b200lap_dev_project_feasible(b200lap_ctx* ctx, const void* C, int is_f64, in
  * reduced-cost matrices (C - u 1^T) - 1 v^T. */
 int b200lap_dev_reduced_costs(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const double* u, const double* v,
                               double* out, double* min_host);
+
+/* Oracle duals by difference constraints -- solvers/dual_computation.py:13-47 (dual_from_matching_diff_constraints):
+ * Bellman-Ford relaxation from v = 0 over the edges p -> j of weight C[r_p, j] - C[r_p, p] built from an optimal
+ * matching x (row -> column, int32 [batch][n], device), every edge evaluated as the reference evaluates it, all n^2
+ * edges of a round at once; returns the column potentials v (double [batch][n], device) and the rounds taken.
+ * B200LAP_ERR_ARG when the relaxation still moves after n - 1 rounds (the reference's "Negative cycle" error). */
+int b200lap_dev_bf_duals(b200lap_ctx* ctx, const void* C, int is_f64, int batch, int n, const int* x, double* v, int* rounds);
 /* features -> OneGNN -> min-trick -> seeded solve without leaving the device. */
 int b200lap_dev_pipeline(b200lap_ctx* ctx, const b200lap_model* model, const void* C, int is_f64, int batch, int n,
                          double eps, int* x, int* y, int* rc, double* u64, double* v64, long long* trace);

@@ -282,12 +282,16 @@ def test_row_features_warp_kernel(emu):
     Cf = np.ascontiguousarray(C, dtype=np.float32)
     feat = np.zeros((n, 21), np.float32)
     topv = np.zeros((n, 16), np.float32)
-    assert lib.b200lap_dev_row_features(ctx, Cf.ctypes.data, 0, 1, n, 16, None, feat.ctypes.data, topv.ctypes.data) == 0
+    _opt(lib, ctx, "feat_impl", 4)                               # the round-1 warp-per-row kernel (the group kernel is the default)
+    try:
+        assert lib.b200lap_dev_row_features(ctx, Cf.ctypes.data, 0, 1, n, 16, None, feat.ctypes.data, topv.ctypes.data) == 0
+    finally:
+        _opt(lib, ctx, "feat_impl", 0)
     feature_close(feat, ref, rtol=1e-4)
     assert np.array_equal(topv, np.sort(Cf, axis=1)[:, :16])
 
 
-@pytest.mark.parametrize("n,group", [(512, 0), (1024, 2), (2048, 4)])
+@pytest.mark.parametrize("n,group", [(512, 0), (1024, 2)])       # four warps per row: tests/test_gpu_round2.py
 def test_row_features_group_kernel(emu, n, group):
     """The group kernel (features_group.cuh: G warps per row, sorted-sample brackets, lane-private byte histograms)
     with its redo hand-over to the CTA kernel, for one, two and four warps per row: uniform, 1e6-fill (count-only
@@ -295,7 +299,7 @@ def test_row_features_group_kernel(emu, n, group):
     from oracle import features_np
     lib, ctx = emu
     rng = np.random.default_rng(n)
-    rows = 96 if n > 512 else n                                  # the emulator is slow: a rectangular slice of rows
+    rows = 96                                                    # the emulator is slow: a slice of rows, the rest parked on a constant
     C = rng.uniform(0, 1, (n, n))
     j = np.arange(n)
     fill = rng.uniform(size=(16, n)) > 0.3
@@ -361,3 +365,62 @@ def test_advanced_dual_sweeps(emu):
         assert mn.value == raw.min() and np.array_equal(out, raw - raw.min() if raw.min() < 0 else raw)
         assert lib.b200lap_reduce_costs(C.ctypes.data, n, u.ctypes.data, v.ctypes.data, 0, None, ctypes.addressof(mn)) == 0
         assert mn.value == raw.min()
+
+
+def _round2_golden():
+    return np.load(os.path.join(HERE, "golden", "round2_golden.npz"))
+
+
+def test_oracle_duals_relaxation_matches_reference(emu):
+    """b200lap_dev_bf_duals (csrc/dualsweep.cuh: Jacobi rounds of the difference-constraint relaxation) + the reference's
+    finishing statements against goldens recorded from the reference's own compute_oracle_duals
+    (solvers/dual_computation.py:13-115): bit-identical u*, v*, with and without the seeded noise."""
+    from scipy.optimize import linear_sum_assignment
+    from solvers.dual_computation import finish_duals
+    lib, ctx = emu
+    g = _round2_golden()
+    for fam in ("uniform", "sparse", "sparse1e6", "metric", "clustered"):
+        C = np.ascontiguousarray(g[f"duals/{fam}/C"])
+        n = C.shape[0]
+        rows, cols = linear_sum_assignment(C)
+        x = np.empty(n, np.int32)
+        x[rows] = cols
+        for dt in (np.float32, np.float64):
+            Cd = np.ascontiguousarray(C.astype(dt))
+            v = np.empty(n, np.float64)
+            rounds = ctypes.c_int(0)
+            assert lib.b200lap_dev_bf_duals(ctx, Cd.ctypes.data, int(dt == np.float64), 1, n, x.ctypes.data, v.ctypes.data, ctypes.byref(rounds)) == 0
+            assert 1 <= rounds.value <= n - 1
+            u, vv, red = finish_duals(C, rows, cols, v.copy())
+            assert np.array_equal(u, g[f"duals/{fam}/u_0"]) and np.array_equal(vv, g[f"duals/{fam}/v_0"]), (fam, dt)
+            np.random.seed(42)
+            un, vn = u + np.random.normal(0, 1e-3, n), vv + np.random.normal(0, 1e-3, n)
+            assert np.array_equal(un, g[f"duals/{fam}/u_1e-3"]) and np.array_equal(vn, g[f"duals/{fam}/v_1e-3"]), fam
+    # a matching that is not optimal has a negative cycle: the relaxation never settles and the call says so
+    C = np.ascontiguousarray(g["duals/uniform/C"])
+    n = C.shape[0]
+    bad = np.roll(np.arange(n, dtype=np.int32), 1)
+    v = np.empty(n, np.float64)
+    assert lib.b200lap_dev_bf_duals(ctx, C.ctypes.data, 1, 1, n, bad.ctypes.data, v.ctypes.data, None) != 0
+
+
+def test_row_features_torch_mode(emu):
+    """feat_torch_mode = the definitions of the reference's compute_row_features_torch (gnn/features.py:246-351:
+    unbiased std / k_std, bincount(argmin) column preference, binary32 near-best threshold), against goldens recorded
+    from the reference function."""
+    lib, ctx = emu
+    g = _round2_golden()
+    _opt(lib, ctx, "feat_torch_mode", 1)
+    try:
+        for fam in ("sparse1e6", "metric", "clustered"):             # all five on the GPU: tests/test_gpu_round2.py
+            C = np.ascontiguousarray(g[f"tfeat/{fam}/C"].astype(np.float32))
+            n = C.shape[0]
+            feat = np.zeros((n, 21), np.float32)
+            assert lib.b200lap_dev_row_features(ctx, C.ctypes.data, 0, 1, n, 0, None, feat.ctypes.data, None) == 0
+            ref = g[f"tfeat/{fam}/feat"]
+            # the reference evaluates this variant in binary32 throughout: its own entropy carries ~1e-6 of absolute
+            # rounding noise (sum of n terms p * log(p + 1e-9) with p up to 1), so that column gets that floor
+            feature_close(np.delete(feat, 5, axis=1), np.delete(ref, 5, axis=1), rtol=1e-4)
+            feature_close(feat[:, 5], ref[:, 5], rtol=1e-4, atol=1e-6)
+    finally:
+        _opt(lib, ctx, "feat_torch_mode", 0)
