@@ -399,32 +399,65 @@ def run_b200(args):
 
     LANES = int(os.environ.get("B200LAP_LANES", "8"))
     ctx.set_overlap(LANES)
+    # N > 1: the job is world x steps batch-units drained from ONE queue (b200lap.WorkQueue: an atomic counter in the
+    # process group's store), unit u = the batch of rank u % world.  Solve times are data dependent, so static blocks
+    # leave the job waiting for the rank with the hardest batch; every rank therefore holds every rank's batch on its
+    # device (one NCCL broadcast each at set-up, outside the timed region) and claims a unit whenever a lane frees up.
+    dynamic = world > 1 and os.environ.get("B200LAP_STATIC_SPLIT", "0") != "1"
+    batches = [Cd]
+    if dynamic:
+        batches = []
+        for b in range(world):
+            t = Cd if b == rank else torch.empty_like(Cd)
+            dist.broadcast(t, src=b)
+            batches.append(t)
+        torch.cuda.synchronize()
     for _ in range(args.warmup):
         out = step_resident()
     ctx.sync()
     barrier()
     launches0 = ctx.launches
     outs = []
+    units_done = args.steps
     with ClockSampler(local) as clk:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(args.steps):
-            outs = (outs + [step_resident()])[-LANES:]
-        ctx.join()                      # lane 0's stream waits for lane 1 on the device ...
-        e1.record(stream)               # ... so this event closes the work of both lanes
+        if dynamic:
+            queue = b200lap.WorkQueue(world * args.steps, name="bench_resident")
+
+            def launch(unit):
+                outs.append(ctx.pipeline(model, batches[unit % world]))
+                del outs[:-LANES]
+                return ctx.last_lane_event()
+            units_done = len(b200lap.drain_queue(queue, launch, in_flight=LANES))
+        else:
+            for _ in range(args.steps):
+                outs = (outs + [step_resident()])[-LANES:]
+        ctx.join()                      # lane 0's stream waits for the other lanes on the device ...
+        e1.record(stream)               # ... so this event closes the work of all lanes
         ctx.sync()
         barrier()
         ms_resident = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
     ctx.set_overlap(False)
-    out = outs[-1]
     for o in outs:
         assert (o[2].cpu().numpy() == 0).all(), o[2]
-        assert torch.equal(o[0], out[0]) and torch.equal(o[1], out[1]), "the two lanes disagree"
+    if not dynamic:
+        out = outs[-1]
+        for o in outs:
+            assert torch.equal(o[0], out[0]) and torch.equal(o[1], out[1]), "the lanes disagree"
+    else:
+        out = step_resident()          # this rank's own batch, for the host-path comparison below
+        ctx.sync()
     t = torch.tensor([ms_resident], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
+    tu = torch.tensor([float(units_done)], dtype=torch.float64, device="cuda")
+    units_all = [torch.zeros_like(tu) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(units_all, tu)
+    units_per_rank = [int(u.item()) for u in units_all] if world > 1 else [args.steps]
     # one batch at a time (latency of a step when nothing else is in flight)
     ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ea.record(stream)
@@ -570,6 +603,8 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "ms_per_step_alone": round(ms_step_alone, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": bench_config(world),
+            "scheduling": ("dynamic: world x steps batch-units drained from one queue (b200lap.WorkQueue), units per rank " + str(units_per_rank))
+                          if dynamic else "static: every rank steps over its own batch",
             "e2e": {"value": round(world * B / e2e_s, 2), "unit": "instances/s", "h2d_bytes_per_step": int(Ch.nbytes),
                     "d2h_bytes_per_step": int(B * n * 8 * 2 + rch.nbytes + 4), "steps": e2e_steps,
                     "api": f"b200lap_pipeline_batch_submit/_wait, {LANES} batches in flight",

@@ -64,6 +64,7 @@ SIGNATURES = {
     "b200lap_project_feasible": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_double, vp]),
     "b200lap_reduce_costs": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp]),
     "b200lap_ctx_lane_stream": (vp, [vp, ctypes.c_int]),
+    "b200lap_ctx_last_lane": (ctypes.c_int, [vp]),
     "b200lap_ctx_join": (ctypes.c_int, [vp]),
     "b200lap_pipeline_batch_submit": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp, vp, ctypes.POINTER(vp)]),
     "b200lap_pipeline_batch_wait": (ctypes.c_int, [vp]),

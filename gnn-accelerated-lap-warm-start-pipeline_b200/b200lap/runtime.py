@@ -324,6 +324,15 @@ class Context:
         self._overlap = lanes
         self.set_option("overlap_steps", lanes)
 
+    def last_lane_event(self):
+        """A CUDA event recorded behind the most recent ``pipeline`` call on the lane it was enqueued on: ``synchronize()``
+        returns when that batch is done (used as the handle of ``b200lap.drain_queue``)."""
+        torch = _torch()
+        lane = int(self.lib.b200lap_ctx_last_lane(self.handle))
+        ev = torch.cuda.Event()
+        ev.record(self.lane_stream(lane) if getattr(self, "_overlap", 0) else self.torch_stream())
+        return ev
+
     def join(self):
         """Lane 0's stream (``torch_stream()``) waits on the device for everything enqueued on lane 1."""
         check(self.lib.b200lap_ctx_join(self.handle), "b200lap_ctx_join", self.lib)

@@ -1,8 +1,13 @@
 """Instance-level sharding across the GPUs of one box.
 
-Instances are independent, so the batch is split into contiguous blocks, one per rank (one process
-per GPU under torchrun); there is no data-path collective.  Results (x, y int32 per instance) are
-gathered onto rank 0 with one ``gather`` over the process group (NCCL on GPUs, gloo in the CPU tests).
+Instances are independent, so there is no data-path collective.  Two ways to hand them out:
+  * ``shard_bounds`` / ``solve_sharded`` -- contiguous static blocks, one per rank (one process per GPU under
+    torchrun); results (x, y int32 per instance) are gathered onto rank 0 with one ``gather`` over the process group
+    (NCCL on GPUs, gloo in the CPU tests);
+  * ``WorkQueue`` -- a shared queue of work units (batches of instances) that the ranks drain dynamically: solve
+    times are data dependent (a sparse-family instance takes twice a uniform one), so with static blocks the slowest
+    rank sets the time of the job.  The queue is one atomic counter in the process group's key-value store
+    (``store.add``), i.e. control-plane traffic only; a rank claims its next unit when one of its lanes frees up.
 """
 from __future__ import annotations
 
@@ -45,3 +50,53 @@ def solve_sharded(batch: int, solve_block: Callable[[int, int], "object"], group
         a, b = shard_bounds(batch, world, r)
         out.append(bucket[r][: b - a])
     return out
+
+
+class WorkQueue:
+    """``total`` work units, claimed one at a time by whichever rank is ready (dynamic distribution
+    instead of static equal splits).  ``store`` is a ``torch.distributed`` store (default: the one of the initialised
+    default process group); without a process group the queue is local.  Every queue of a job needs its own ``name``."""
+
+    def __init__(self, total: int, name: str = "b200lap_queue", store=None):
+        import torch.distributed as dist
+        self.total, self.key, self._local = int(total), f"{name}/next", 0
+        self.store = store
+        if self.store is None and dist.is_available() and dist.is_initialized():
+            from torch.distributed import distributed_c10d
+            self.store = distributed_c10d._get_default_store()
+        self.claimed: List[int] = []
+
+    def claim(self) -> Optional[int]:
+        """The next unclaimed unit id, or None when the queue is drained."""
+        if self.store is None:
+            k = self._local
+            self._local += 1
+        else:
+            k = int(self.store.add(self.key, 1)) - 1
+        if k >= self.total:
+            return None
+        self.claimed.append(k)
+        return k
+
+
+def drain_queue(queue: "WorkQueue", launch: Callable[[int], "object"], in_flight: int = 1, wait: Optional[Callable[["object"], None]] = None):
+    """Claims units until the queue is empty, keeping at most ``in_flight`` launched units outstanding on this rank:
+    ``launch(unit)`` enqueues the unit's work asynchronously and returns a handle, ``wait(handle)`` blocks until it is
+    done (default: ``handle.synchronize()``, e.g. a CUDA event).  The back-pressure is what makes the distribution
+    dynamic -- a rank only claims when one of its lanes is free.  Returns the units this rank processed."""
+    pending: List[Tuple[int, object]] = []
+    done: List[int] = []
+    wait = wait or (lambda h: h.synchronize())
+    while True:
+        if len(pending) >= max(1, in_flight):
+            u, h = pending.pop(0)
+            wait(h)
+            done.append(u)
+        unit = queue.claim()
+        if unit is None:
+            break
+        pending.append((unit, launch(unit)))
+    for u, h in pending:
+        wait(h)
+        done.append(u)
+    return done

@@ -93,6 +93,7 @@ struct b200lap_ctx {
     int active_lane = 0;
     int overlap_steps = 0;       // option: number of lanes independent whole-pipeline calls rotate through (0/1 = off, up to 8)
     long long lane_calls = 0;
+    int last_lane = 0;           // lane of the most recent whole-pipeline call (b200lap_ctx_last_lane)
     int lanes() const { return overlap_steps < 2 ? 1 : (overlap_steps > kMaxLanes ? kMaxLanes : overlap_steps); }
     void use_lane(int l) {
         if (l == active_lane) return;
@@ -356,6 +357,8 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
     // 512-thread CTAs keep the per-thread state (4 registers per column) under the 128-register budget.
     a.regpath = (ctx->solver_regpath && cluster == 1 && vec_ok(C, inst_stride, ld, n)) ? 1 : 0;
     if (a.regpath && ctx->solver_threads <= 0 && T > 512 && n <= 8192) T = 512;
+    // (256-thread CTAs -- two instances per SM -- were measured for the many-batches-in-flight case: 27.9 vs 27.8 ms per
+    //  64 x 2048 step at 8 lanes, but 113 vs 83 ms for a batch alone and a slower host path; not used.  tools/solver_threads_exp.py)
     a.kcap = ctx->solver_kcap; a.pipe = ctx->solver_pipe;
     const int per_thread = (n + T - 1) / T;      // row entries a thread keeps in registers per step
 #define SOLVE(MAXC_)                                                                                                       \
@@ -481,6 +484,8 @@ void b200lap_ctx_destroy(b200lap_ctx* ctx) {
 }
 
 void* b200lap_ctx_stream(b200lap_ctx* ctx) { return ctx ? (void*)ctx->lane_stream(0) : nullptr; }
+int b200lap_ctx_last_lane(b200lap_ctx* ctx) { return ctx ? ctx->last_lane : 0; }
+
 void* b200lap_ctx_lane_stream(b200lap_ctx* ctx, int lane) {
     return (ctx && lane >= 0 && lane < b200lap_ctx::kMaxLanes) ? (void*)ctx->lane_stream(lane) : nullptr;
 }

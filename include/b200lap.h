@@ -65,6 +65,7 @@ int b200lap_ctx_sync(b200lap_ctx* ctx);               /* waits for both lanes */
  * occupies 64 of the 148 SMs).  Results of such calls are complete after b200lap_ctx_sync, or -- for work enqueued on
  * lane 0's stream -- after b200lap_ctx_join, which makes lane 0's stream wait for lane 1 on the device. */
 void* b200lap_ctx_lane_stream(b200lap_ctx* ctx, int lane);
+int b200lap_ctx_last_lane(b200lap_ctx* ctx);            /* lane the most recent b200lap_dev_pipeline call was enqueued on */
 int b200lap_ctx_join(b200lap_ctx* ctx);
 /* Tuning / test options (0 = automatic unless stated): solver_threads, solver_cluster (CTAs per instance: 1 = single
  * CTA, 2/4/8 = thread-block cluster; auto = 8 from solver_cluster_min_n = 8192 on), force_global_state,

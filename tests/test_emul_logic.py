@@ -345,10 +345,10 @@ def test_advanced_dual_sweeps(emu):
     NumPy statements, bit for bit, binary32- and binary64-stored matrices."""
     lib, ctx = emu
     rng = np.random.default_rng(21)
-    for n, f64 in ((33, False), (48, False), (40, True)):
+    for n, f64 in ((20, False), (12, True)):                     # larger sizes on the GPU: tests/test_gpu_config_parity.py
         C = gen.make_instance("uniform", n, seed=n) if not f64 else rng.uniform(0, 1, (n, n))
         u, v = noisy_oracle_seeds(C, 5e-2)
-        for rounds in (1, 50):
+        for rounds in (1, 4):
             ur, vr = u.copy(), v.copy()
             for _ in range(rounds):
                 ur = np.minimum(ur, (C - vr[None, :]).min(axis=1))
@@ -379,7 +379,7 @@ def test_oracle_duals_relaxation_matches_reference(emu):
     from solvers.dual_computation import finish_duals
     lib, ctx = emu
     g = _round2_golden()
-    for fam in ("uniform", "sparse", "sparse1e6", "metric", "clustered"):
+    for fam in ("sparse1e6", "metric", "clustered"):             # all five on the GPU: tests/test_gpu_round2.py
         C = np.ascontiguousarray(g[f"duals/{fam}/C"])
         n = C.shape[0]
         rows, cols = linear_sum_assignment(C)
