@@ -78,6 +78,7 @@ struct b200lap_ctx {
     int feat_ctas = 0;
     const int* feat_redo_count = nullptr;   // device counter of the last row-feature call (rows the fast kernel handed to the fall-back)
     cudaStream_t feat_redo_stream = nullptr;
+    int feat_stream = 0;         // option: 0 = auto, 1 = stream the row from global memory (no staging), 2 = stage it in shared memory
     int feat_torch_mode = 0;     // option: 1 = the definitions of compute_row_features_torch (gnn/features.py:246-351)
     int feat_group = 0;          // option: warps per row of the group kernel (0 = auto: n / 2048, 1..8 forces; needs n = 32 * G * {16, 32, 64, 128})
     int sm_count = 148;
@@ -538,6 +539,7 @@ int b200lap_ctx_set_option(b200lap_ctx* ctx, const char* key, long long value) {
     else if (k == "feat_nsamp") ctx->feat_nsamp = (int)value;
     else if (k == "feat_ctas") ctx->feat_ctas = (int)value;
     else if (k == "feat_group") ctx->feat_group = (int)value;
+    else if (k == "feat_stream") ctx->feat_stream = (int)value;
     else if (k == "feat_torch_mode") ctx->feat_torch_mode = (int)value;
     else return fail(B200LAP_ERR_ARG, "unknown option " + k);
     return 0;

@@ -28,15 +28,15 @@
 namespace b200lap {
 
 constexpr int kGrpSamp = 256;     // sample keys per warp (8 per lane)
-constexpr int kGrpBins = 64;      // bins of the lane-private byte histograms
+constexpr int kGrpBinsMax = 128;  // bins of the lane-private byte histograms: 64, or 128 for rows of >= 128 entries per lane
 constexpr int kGrpTiny = 64;
 constexpr int kGrpCand = 128;
 constexpr int kGrpPart = 12;
 
-template <int G>
+template <int G, int BINS>
 struct __align__(16) GrpShared {
     float part[G][kGrpPart];
-    int cnts[G][kGrpBins];
+    int cnts[G][BINS];
     float tiny[kGrpTiny];
     float cand[kGrpCand];
     float sorted[32];
@@ -45,11 +45,13 @@ struct __align__(16) GrpShared {
 };
 
 __host__ __device__ constexpr int grp_parities(int G) { return G > 1 ? 2 : 1; }
-// bytes of dynamic shared memory for Q groups of G warps, rows of n floats, list capacity kcap per lane
+__host__ __device__ constexpr int grp_bins(int EPL) { return EPL >= 128 ? 128 : 64; }
+// bytes of dynamic shared memory for Q groups of G warps, rows of n floats (none when the row is streamed from
+// global memory instead of being staged), `bins` histogram bins, list capacity kcap per lane
 template <int G>
-__host__ __device__ constexpr size_t grp_smem_bytes(int Q, int n, int kcap) {
-    return 128 + (size_t)Q * grp_parities(G) * sizeof(GrpShared<G>) + (size_t)Q * G * ((size_t)kGrpBins * 32 + (size_t)kcap * 128) +
-           (size_t)Q * n * 4;
+__host__ __device__ constexpr size_t grp_smem_bytes(int Q, int n, int kcap, int bins, bool stream) {
+    return 128 + (size_t)Q * grp_parities(G) * (bins == 128 ? sizeof(GrpShared<G, 128>) : sizeof(GrpShared<G, 64>)) +
+           (size_t)Q * G * ((size_t)bins * 32 + (size_t)kcap * 128) + (stream ? 0 : (size_t)Q * n * 4);
 }
 
 // ---- group barrier (G warps) ------------------------------------------------------------------------
@@ -131,21 +133,22 @@ __device__ __forceinline__ int dp4a_ones(unsigned w, int acc) {
 
 // Exact keys of the list ranks k1 <= k2 = k1 + {0, 1} of the group's lane-private lists (keys in [lo, hi]).
 // Every warp of the group calls it and gets the same answer; false = give up (group-uniform).
-template <int G>
-__device__ __forceinline__ bool grp_select(GrpShared<G>& S, unsigned char* bh, const float* list, const ListCursor& cur, int q, int w, float lo, float hi,
+template <int G, int BINS>
+__device__ __forceinline__ bool grp_select(GrpShared<G, BINS>& S, unsigned char* bh, const float* list, const ListCursor& cur, int q, int w, float lo, float hi,
                                            int k1, int k2, float& ra, float& rb)
 {
+    constexpr int NB = BINS / 32;                     // bins per lane: lane owns bins lane, lane + 32, ...
     const int lane = lane_id();
-    const float scale = (float)kGrpBins / (hi - lo);
+    const float scale = (float)BINS / (hi - lo);
     {
         const uint4 z = {0u, 0u, 0u, 0u};
         uint4* b4 = reinterpret_cast<uint4*>(bh);
 #pragma unroll
-        for (int i = 0; i < kGrpBins * 32 / 16 / 32; ++i) b4[i * 32 + lane] = z;
+        for (int i = 0; i < BINS / 16; ++i) b4[i * 32 + lane] = z;
     }
     if (w == 0 && lane == 0) S.ntiny = 0;
     __syncwarp();
-    auto bin_of = [&](float x) { const int b = (int)((x - lo) * scale); return b > kGrpBins - 1 ? kGrpBins - 1 : b; };
+    auto bin_of = [&](float x) { const int b = (int)((x - lo) * scale); return b > BINS - 1 ? BINS - 1 : b; };
     const int mycnt = cur.count(), maxcnt = warp_max_i(mycnt);
     const float* mylist = list + lane;
     for (int t = 0; t < maxcnt; ++t) {
@@ -155,39 +158,55 @@ __device__ __forceinline__ bool grp_select(GrpShared<G>& S, unsigned char* bh, c
         }
     }
     __syncwarp();
-    int c0 = 0, c1 = 0;   // bins lane and lane + 32
-    {
-        const uint4* r0 = reinterpret_cast<const uint4*>(bh + lane * 32);
-        const uint4* r1 = reinterpret_cast<const uint4*>(bh + (lane + 32) * 32);
-        const uint4 a0 = r0[0], a1 = r0[1], b0 = r1[0], b1 = r1[1];
-        c0 = dp4a_ones(a0.x, c0); c0 = dp4a_ones(a0.y, c0); c0 = dp4a_ones(a0.z, c0); c0 = dp4a_ones(a0.w, c0);
-        c0 = dp4a_ones(a1.x, c0); c0 = dp4a_ones(a1.y, c0); c0 = dp4a_ones(a1.z, c0); c0 = dp4a_ones(a1.w, c0);
-        c1 = dp4a_ones(b0.x, c1); c1 = dp4a_ones(b0.y, c1); c1 = dp4a_ones(b0.z, c1); c1 = dp4a_ones(b0.w, c1);
-        c1 = dp4a_ones(b1.x, c1); c1 = dp4a_ones(b1.y, c1); c1 = dp4a_ones(b1.z, c1); c1 = dp4a_ones(b1.w, c1);
+    int c[NB], inc[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const uint4* r0 = reinterpret_cast<const uint4*>(bh + (lane + 32 * k) * 32);
+        const uint4 a0 = r0[0], a1 = r0[1];
+        int t = 0;
+        t = dp4a_ones(a0.x, t); t = dp4a_ones(a0.y, t); t = dp4a_ones(a0.z, t); t = dp4a_ones(a0.w, t);
+        t = dp4a_ones(a1.x, t); t = dp4a_ones(a1.y, t); t = dp4a_ones(a1.z, t); t = dp4a_ones(a1.w, t);
+        c[k] = t;
     }
     if (G > 1) {
-        S.cnts[w][lane] = c0; S.cnts[w][lane + 32] = c1;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) S.cnts[w][lane + 32 * k] = c[k];
         grp_sync<G>(q);
-        c0 = 0; c1 = 0;
 #pragma unroll
-        for (int g = 0; g < G; ++g) { c0 += S.cnts[g][lane]; c1 += S.cnts[g][lane + 32]; }
-    }
-    // inclusive scans in bin order (0..31 on c0, then 32..63 on c1)
-    int i0 = c0, i1 = c1;
+        for (int k = 0; k < NB; ++k) {
+            int t = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t0 = __shfl_up_sync(kFull, i0, o), t1 = __shfl_up_sync(kFull, i1, o);
-        if (lane >= o) { i0 += t0; i1 += t1; }
+            for (int g = 0; g < G; ++g) t += S.cnts[g][lane + 32 * k];
+            c[k] = t;
+        }
     }
-    i1 += __shfl_sync(kFull, i0, 31);
+    // inclusive scans in bin order (segment k holds bins 32 k .. 32 k + 31)
+    int carry = 0;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        int v = c[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, v, o);
+            if (lane >= o) v += t;
+        }
+        inc[k] = v + carry;
+        carry = __shfl_sync(kFull, inc[k], 31);
+    }
     auto locate = [&](int k, int& b, int& before, int& cnt) {
-        const unsigned m0 = __ballot_sync(kFull, k < i0), m1 = __ballot_sync(kFull, k < i1);
-        const bool first = m0 != 0u;
-        const int src = first ? __ffs((int)m0) - 1 : (m1 ? __ffs((int)m1) - 1 : 31);
-        const int incl = __shfl_sync(kFull, first ? i0 : i1, src);
-        cnt = __shfl_sync(kFull, first ? c0 : c1, src);
-        before = incl - cnt;
-        b = first ? src : 32 + src;
+        b = BINS - 1; before = 0; cnt = 0;
+        bool found = false;
+#pragma unroll
+        for (int sgm = 0; sgm < NB; ++sgm) {
+            const unsigned m = __ballot_sync(kFull, k < inc[sgm]);
+            if (!found && m != 0u) {
+                const int src = __ffs((int)m) - 1;
+                cnt = __shfl_sync(kFull, c[sgm], src);
+                before = __shfl_sync(kFull, inc[sgm], src) - cnt;
+                b = 32 * sgm + src;
+                found = true;
+            }
+        }
     };
     int b1, bb1, n1, b2, bb2, n2;
     locate(k1, b1, bb1, n1);
@@ -217,10 +236,15 @@ __device__ __forceinline__ bool grp_select(GrpShared<G>& S, unsigned char* bh, c
     return true;
 }
 
-template <int G, int EPL>
+// STREAM: the row is not staged in shared memory; pass 1 reads it from global memory (DRAM), pass 2 and the rare extra
+// pass read it again (L2: the row is 32 G EPL x 4 bytes and was read a moment ago).  That frees the 64 KB a row of
+// n = 16384 takes, so such rows can be owned by FEWER warps (the per-warp bookkeeping -- sample sort, list selections,
+// reductions -- is paid per warp, not per entry) while 16 warps stay resident.
+template <int G, int EPL, bool STREAM>
 __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
 {
     B200LAP_DYN_SMEM(smem_raw);
+    constexpr int BINS = grp_bins(EPL);
     constexpr int NG = EPL / 4;                          // float4 groups per lane
     constexpr int P = grp_parities(G);
     constexpr int SEG = EPL * 32;                        // floats per warp segment
@@ -228,11 +252,11 @@ __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
     const int Q = (int)(blockDim.x >> 5) / G;            // groups in this CTA
     const int q = warp_id() / G, w = warp_id() % G;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    GrpShared<G>* SH = reinterpret_cast<GrpShared<G>*>(smem_raw + 128) + (size_t)q * P;
-    unsigned char* warp_base = smem_raw + 128 + (size_t)Q * P * sizeof(GrpShared<G>) + (size_t)warp_id() * ((size_t)kGrpBins * 32 + (size_t)a.kcap * 128);
+    GrpShared<G, BINS>* SH = reinterpret_cast<GrpShared<G, BINS>*>(smem_raw + 128) + (size_t)q * P;
+    unsigned char* warp_base = smem_raw + 128 + (size_t)Q * P * sizeof(GrpShared<G, BINS>) + (size_t)warp_id() * ((size_t)BINS * 32 + (size_t)a.kcap * 128);
     unsigned char* bh = warp_base;
-    float* list = reinterpret_cast<float*>(warp_base + kGrpBins * 32);
-    float* rowbuf = reinterpret_cast<float*>(smem_raw + 128 + (size_t)Q * P * sizeof(GrpShared<G>) + (size_t)Q * G * ((size_t)kGrpBins * 32 + (size_t)a.kcap * 128)) + (size_t)q * n;
+    float* list = reinterpret_cast<float*>(warp_base + BINS * 32);
+    float* rowbuf = reinterpret_cast<float*>(smem_raw + 128 + (size_t)Q * P * sizeof(GrpShared<G, BINS>) + (size_t)Q * G * ((size_t)BINS * 32 + (size_t)a.kcap * 128)) + (STREAM ? 0 : (size_t)q * n);
     const float4* seg4 = reinterpret_cast<const float4*>(rowbuf + (size_t)w * SEG);
 
     const long long total_rows = (long long)a.batch * n;
@@ -249,13 +273,14 @@ __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
 
     auto row_src = [&](long long r) { return a.C + (r / n) * a.inst_stride + (r % n) * (long long)a.ld + (size_t)w * SEG; };
 #ifndef B200LAP_EMUL
-    if (threadIdx.x == 0) {
+    if (!STREAM && threadIdx.x == 0) {
         for (int i = 0; i < Q; ++i) mbar_init(&full[i], G);
         mbar_fence_init();
     }
     __syncthreads();
     // request this warp's segment of row r (the buffer segment must no longer be read by anybody)
     auto request = [&](long long r) {
+        if (STREAM) return;
         __syncwarp();
         if (lane == 0) {
             fence_proxy_async();
@@ -266,6 +291,7 @@ __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
     unsigned phase = 0u;
 #else
     auto request = [&](long long r) {
+        if (STREAM) return;
         __syncwarp();
         const float* src = row_src(r);
         float* dst = rowbuf + (size_t)w * SEG;
@@ -278,14 +304,18 @@ __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
     int par = 0;
     for (; r < total_rows; r += ngroups) {
         const long long rnext = r + ngroups;
-        GrpShared<G>& S = SH[P == 2 ? par : 0];
+        GrpShared<G, BINS>& S = SH[P == 2 ? par : 0];
         par ^= 1;
 #ifndef B200LAP_EMUL
-        mbar_wait(&full[q], phase); phase ^= 1u;
+        if (!STREAM) { mbar_wait(&full[q], phase); phase ^= 1u; }
 #else
-        grp_sync<G>(q);
+        if (!STREAM) grp_sync<G>(q);
 #endif
         const int b = (int)(r / n), row = (int)(r % n);
+        const float* grow = a.C + (size_t)b * a.inst_stride + (size_t)row * a.ld;             // the row in global memory
+        const float4* gseg4 = reinterpret_cast<const float4*>(grow + (size_t)w * SEG);
+        auto ld_pass1 = [&](int idx) { return STREAM ? __ldg(gseg4 + idx) : seg4[idx]; };     // DRAM: keep the line for pass 2
+        auto ld_again = [&](int idx) { return STREAM ? __ldcs(gseg4 + idx) : seg4[idx]; };    // L2 hit, last use
         const float4* cm = reinterpret_cast<const float4*>(a.colmin + (size_t)b * n + (size_t)w * SEG);
         bool redo = false;
 
@@ -294,7 +324,8 @@ __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int i = (j * 32 + lane) * G + w;
-            sx[j] = rowbuf[i * STRIDE + ((lane >> 2) & (STRIDE - 1))];
+            const int pos = i * STRIDE + ((lane >> 2) & (STRIDE - 1));
+            sx[j] = STREAM ? __ldg(grow + pos) : rowbuf[pos];
         }
         warp_bitonic_sort<8>(sx);
         float L = sorted_at<8>(sx, t1), H = sorted_at<8>(sx, t2);
@@ -320,7 +351,7 @@ __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
             constexpr bool TIE = decltype(tie_tag)::value;
 #pragma unroll 4
             for (int g = 0; g < NG; ++g) {
-                const float4 c4 = seg4[g * 32 + lane];
+                const float4 c4 = ld_pass1(g * 32 + lane);
                 const float4 m4 = __ldg(cm + g * 32 + lane);
                 const float c[4] = {c4.x, c4.y, c4.z, c4.w};
                 const float m[4] = {m4.x, m4.y, m4.z, m4.w};
@@ -378,7 +409,7 @@ __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
         float ma = L, mb = L;
         if (!redo && !(r1 >= below && r2 < below + inside)) { redo = true; why = 2; }
         if (!__any_sync(kFull, redo) && !__all_sync(kFull, tie)) {
-            if (!grp_select<G>(S, bh, list, cur, q, w, L, bracket_upper(L, H - L), r1 - below, r2 - below, ma, mb)) { redo = true; why = 3; }
+            if (!grp_select<G, BINS>(S, bh, list, cur, q, w, L, bracket_upper(L, H - L), r1 - below, r2 - below, ma, mb)) { redo = true; why = 3; }
         }
         if (__any_sync(kFull, redo)) {
             // the row buffer is free: get the next row, hand this one to the CTA kernel
@@ -420,7 +451,7 @@ __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
             constexpr bool TIE = decltype(tie_tag)::value;
 #pragma unroll 4
             for (int g = 0; g < NG; ++g) {
-                const float4 c4 = seg4[g * 32 + lane];
+                const float4 c4 = ld_again(g * 32 + lane);
                 const float c[4] = {c4.x, c4.y, c4.z, c4.w};
                 if (!TIE && cur.beyond(a.kcap - 4)) { wlim2 = 0u; ovf2 = true; }
 #pragma unroll
@@ -486,13 +517,13 @@ __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
                 // the common case (ties at the row minimum, e.g. clamped-at-zero rows): only the near-best count
 #pragma unroll 4
                 for (int g = 0; g < NG; ++g) {
-                    const float4 c4 = seg4[g * 32 + lane];
+                    const float4 c4 = ld_again(g * 32 + lane);
                     nnear += (c4.x <= near_thr) + (c4.y <= near_thr) + (c4.z <= near_thr) + (c4.w <= near_thr);
                 }
             } else {
 #pragma unroll 2
                 for (int g = 0; g < NG; ++g) {
-                    const float4 c4 = seg4[g * 32 + lane];
+                    const float4 c4 = ld_again(g * 32 + lane);
                     const float c[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -533,7 +564,7 @@ __global__ void __launch_bounds__(512, 1) k_row_features_group(FeatSmemArgs a)
         // ---- MAD
         float da = L2, db2 = L2;
         if (!__all_sync(kFull, tie2)) {
-            if (!grp_select<G>(S, bh, list, cur, q, w, L2, bracket_upper(L2, H2 - L2), r1 - below2, r2 - below2, da, db2)) {
+            if (!grp_select<G, BINS>(S, bh, list, cur, q, w, L2, bracket_upper(L2, H2 - L2), r1 - below2, r2 - below2, da, db2)) {
                 if (w == 0 && lane == 0) { a.redo_list[atomicAdd(a.redo_count, 1)] = (int)r; atomicAdd(a.redo_count + 3, 1); }
                 continue;
             }

@@ -291,8 +291,8 @@ def test_row_features_warp_kernel(emu):
     assert np.array_equal(topv, np.sort(Cf, axis=1)[:, :16])
 
 
-@pytest.mark.parametrize("n,group", [(512, 0), (1024, 2)])       # four warps per row: tests/test_gpu_round2.py
-def test_row_features_group_kernel(emu, n, group):
+@pytest.mark.parametrize("n,group,stream", [(512, 0, 0), (512, 0, 1), (1024, 2, 0)])       # other shapes: tests/test_gpu_round2.py
+def test_row_features_group_kernel(emu, n, group, stream):
     """The group kernel (features_group.cuh: G warps per row, sorted-sample brackets, lane-private byte histograms)
     with its redo hand-over to the CTA kernel, for one, two and four warps per row: uniform, 1e6-fill (count-only
     tie variant), clamped-at-zero rows, metric-style isolated minima, ties around the median, sorted / periodic rows."""
@@ -324,6 +324,7 @@ def test_row_features_group_kernel(emu, n, group):
     feat = np.zeros((n, 21), np.float32)
     topv = np.zeros((n, 16), np.float32)
     _opt(lib, ctx, "feat_group", group)
+    _opt(lib, ctx, "feat_stream", stream)
     try:
         if rows < n:
             # only the first `rows` rows matter: park the rest on the constant row so the emulator skips their lists
@@ -334,6 +335,7 @@ def test_row_features_group_kernel(emu, n, group):
         redo = lib.b200lap_ctx_feature_redo_rows(ctx)
     finally:
         _opt(lib, ctx, "feat_group", 0)
+        _opt(lib, ctx, "feat_stream", 0)
     print("rows handed to the fall-back kernel:", redo)
     assert 0 <= redo <= 16, redo          # the adversarial rows may give up; the family rows must not
     feature_close(feat[:rows], ref, rtol=1e-4)

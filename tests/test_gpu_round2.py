@@ -114,12 +114,13 @@ def test_row_features_torch_variant_at_bench_size():
     assert torch.equal(f[:, 11].float(), (C <= thr).float().mean(dim=1))
 
 
-@pytest.mark.parametrize("n,group", [(512, 0), (1024, 0), (1024, 2), (2048, 0), (2048, 4), (4096, 0), (8192, 0), (16384, 0), (16384, 4)])
-def test_group_row_feature_kernel_every_shape(ctx, n, group):
+@pytest.mark.parametrize("n,group,stream", [(512, 0, 0), (512, 0, 1), (1024, 0, 0), (1024, 2, 0), (2048, 0, 0), (2048, 0, 1), (2048, 4, 0), (4096, 0, 0),
+                                            (4096, 1, 1), (4096, 2, 1), (8192, 0, 0), (8192, 4, 2), (8192, 4, 1), (16384, 0, 0), (16384, 8, 2), (16384, 2, 1), (16384, 4, 1)])
+def test_group_row_feature_kernel_every_shape(ctx, n, group, stream):
     """features_group.cuh for every (warps per row, entries per lane) instantiation: mixed-family rows + adversarial rows,
     exact order statistics / top-k, 1e-4 features; the adversarial rows may go through the fall-back, the family rows must not."""
     import torch
-    rng = np.random.default_rng(n + group)
+    rng = np.random.default_rng(n + group + stream)
     fams = ("uniform", "sparse", "metric", "clustered")
     rows_per = 24
     C = np.empty((n, n))
@@ -151,12 +152,14 @@ def test_group_row_feature_kernel_every_shape(ctx, n, group):
     ref[:, 12] = (C[pick] == C.min(axis=0)[None, :]).mean(axis=1)
     ref[:, 13:] = features_np.positional_terms(n)[pick]
     ctx.set_option("feat_group", group)
+    ctx.set_option("feat_stream", stream)
     try:
         feat, topv = ctx.row_features(torch.from_numpy(C.astype(np.float32)).cuda(), topk=16)
         ctx.sync()
         redo = ctx.feature_redo_rows()
     finally:
         ctx.set_option("feat_group", 0)
+        ctx.set_option("feat_stream", 0)
     # (a forced non-default shape may crowd the 64-key target bin more often: 128 entries per lane at n = 16384)
     assert 0 <= redo <= max(16, n // (50 if group else 100)), redo
     feature_close(feat[0].cpu().numpy()[pick], ref, rtol=1e-4)

@@ -11,7 +11,7 @@ from solvers import generators as gen
 
 ctx = b200lap.default_context(0)
 stream = ctx.torch_stream()
-OPTS = ("feat_impl", "feat_group", "feat_ctas")
+OPTS = ("feat_impl", "feat_group", "feat_ctas", "feat_stream")
 
 def timed(fn, reps=10):
     fn(); fn(); ctx.sync()
@@ -26,13 +26,13 @@ def setopts(**kw):
 
 g = torch.Generator(device="cuda").manual_seed(42)
 cases = [("n2048x64", torch.from_numpy(np.stack([c for _, c in gen.mixed_batch(2048, 64, first_seed=42)]).astype(np.float32)).cuda(),
-          [dict(feat_impl=4), dict(), dict(feat_ctas=12), dict(feat_ctas=8), dict(feat_group=2), dict(feat_group=4)]),
+          [dict(feat_impl=4), dict(), dict(feat_stream=1), dict(feat_stream=2)]),
          ("n16384x1", torch.rand((16384, 16384), generator=g, device="cuda", dtype=torch.float32),
-          [dict(feat_impl=3), dict(), dict(feat_group=4), dict(feat_group=8, feat_ctas=1)]),
+          [dict(feat_impl=3), dict(), dict(feat_group=8, feat_stream=2), dict(feat_group=4, feat_stream=1), dict(feat_group=2, feat_stream=1), dict(feat_group=8, feat_stream=1)]),
          ("n4096x16", torch.from_numpy(np.stack([c for _, c in gen.mixed_batch(4096, 16, first_seed=42)]).astype(np.float32)).cuda(),
-          [dict(feat_impl=3), dict(), dict(feat_group=1), dict(feat_group=4)]),
+          [dict(feat_impl=3), dict(), dict(feat_group=2, feat_stream=2), dict(feat_group=1, feat_stream=1), dict(feat_group=2, feat_stream=1)]),
          ("n8192x4", torch.rand((4, 8192, 8192), generator=g, device="cuda", dtype=torch.float32),
-          [dict(feat_impl=3), dict(), dict(feat_group=2), dict(feat_group=8)]),
+          [dict(feat_impl=3), dict(), dict(feat_group=4, feat_stream=2), dict(feat_group=2, feat_stream=1), dict(feat_group=4, feat_stream=1)]),
          ("n512x256", torch.rand((256, 512, 512), generator=g, device="cuda", dtype=torch.float32), [dict(feat_impl=4), dict()]),
          ("n1024x128", torch.rand((128, 1024, 1024), generator=g, device="cuda", dtype=torch.float32), [dict(feat_impl=4), dict()])]
 for name, C, grid in cases:
