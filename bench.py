@@ -399,11 +399,13 @@ def run_b200(args):
 
     LANES = int(os.environ.get("B200LAP_LANES", "8"))
     ctx.set_overlap(LANES)
-    # N > 1: the job is world x steps batch-units drained from ONE queue (b200lap.WorkQueue: an atomic counter in the
-    # process group's store), unit u = the batch of rank u % world.  Solve times are data dependent, so static blocks
-    # leave the job waiting for the rank with the hardest batch; every rank therefore holds every rank's batch on its
-    # device (one NCCL broadcast each at set-up, outside the timed region) and claims a unit whenever a lane frees up.
-    dynamic = world > 1 and os.environ.get("B200LAP_STATIC_SPLIT", "0") != "1"
+    # N > 1, optional (B200LAP_DYNAMIC_QUEUE=1): the job as world x steps batch-units drained from ONE queue
+    # (b200lap.WorkQueue: an atomic counter in the process group's store), unit u = the batch of rank u % world; every rank
+    # then holds every rank's batch on its device (one NCCL broadcast each at set-up, outside the timed region) and claims a
+    # unit whenever a lane frees up.  Measured at N = 2 (profiles/r02_bench_2gpu_*.json): the ranks' mixed-family batches are
+    # statistically alike, both ranks end up with the same number of units and the claim back-pressure costs 5 %
+    # (4216 vs 4442 inst/s), so the default stays the static split; the queue is for skewed batches.
+    dynamic = world > 1 and os.environ.get("B200LAP_DYNAMIC_QUEUE", "0") == "1"
     batches = [Cd]
     if dynamic:
         batches = []
