@@ -185,3 +185,45 @@ def test_dataset_loader_feeds_the_pipeline(tmp_path, ctx):
     for k in range(3):
         cost, xr, _ = lap.lapjv(items[k][0])
         assert np.isclose(items[k][0][np.arange(512), x[k].cpu().numpy()].sum(), cost, rtol=1e-9)
+
+
+def test_broadly_violating_seeds_are_projected_without_a_cliff(ctx):
+    """seeds that violate u_i + v_j <= c_ij almost everywhere fire the Gauss-Seidel projection ~n^2 times.
+    The warp-level row walk keeps that at tens of milliseconds (the CTA-wide search it replaced took seconds), and the
+    result stays the reference's, tie-breaking included."""
+    import time
+    import oracle
+    import torch
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libreflap.so did not travel")
+    n = 2048
+    C = gen.make_instance("uniform", n, seed=77)
+    u = C.max(axis=1) + 0.25                      # every entry violates under v = 0
+    v = np.zeros(n)
+    xr, yr, cr = oracle.ref_lapjv_seeded(C, u, v)
+    Cd = torch.from_numpy(C.astype(np.float32)).cuda()
+    ud, vd = torch.from_numpy(u).cuda()[None], torch.from_numpy(v).cuda()[None]
+    ctx.solve_seeded(Cd, ud, vd); ctx.sync()      # warm
+    t0 = time.perf_counter()
+    x, y, rc, tr = ctx.solve_seeded(Cd, ud, vd, want_trace=True)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    assert int(rc[0]) == 0
+    assert np.array_equal(x[0].cpu().numpy(), xr) and np.array_equal(y[0].cpu().numpy(), yr)
+    assert int(tr[0, 0]) > 50_000                 # the projection did fire broadly (the first rows pull v down for the later ones)
+    assert dt < 1.5, dt
+
+
+@pytest.mark.parametrize("fam,n,seed", [("uniform", 2048, 101), ("sparse", 2048, 102), ("metric", 2048, 103), ("clustered", 2048, 104),
+                                        ("sparse1e6", 2048, 105), ("clustered", 8192, 106), ("uniform", 16384, 107)])
+def test_row_features_match_the_reference_at_full_size(ctx, fam, n, seed):
+    """Goldens recorded from the REFERENCE's compute_row_features on full-size instances (tests/golden/
+    make_big_feature_golden.py): the sizes where the group kernel's sampled brackets and multi-warp groups run.  The
+    instance is rebuilt from (family, n, seed); 1e-4 on every feature of the stored rows."""
+    import torch
+    g = np.load(os.path.join(HERE, "golden", "feature_rows_golden.npz"))
+    rows, ref = g[f"{fam}/{n}/{seed}/rows"], g[f"{fam}/{n}/{seed}/feat"]
+    C = gen.make_instance(fam, n, seed=seed)
+    feat, _ = ctx.row_features(torch.from_numpy(C.astype(np.float32)).cuda(), topk=16)
+    ctx.sync()
+    feature_close(feat[0].cpu().numpy()[rows], ref, rtol=1e-4)
