@@ -13,6 +13,7 @@
 // of the handful of CUDA runtime calls api.cu makes (malloc/free/memcpy/memset/streams as
 // synchronous host operations).  Blocks run sequentially; blockDim.x must be a multiple of 32.
 #pragma once
+#include <setjmp.h>
 #include <ucontext.h>
 #include <algorithm>
 #include <cassert>
@@ -57,9 +58,13 @@ namespace emul {
 
 constexpr size_t kStack = 256 * 1024;
 
+// Fibers are created with makecontext and switched with _setjmp / _longjmp afterwards: swapcontext saves and restores
+// the signal mask with a system call on every switch, which dominated the run time of the CPU suite.
 struct Fiber {
     ucontext_t ctx;
-    std::vector<unsigned char> stack;
+    jmp_buf jb;
+    bool started = false;
+    unsigned char* stack = nullptr;      // from a process-wide pool, reused by every block (never zero-filled)
     bool done = false;
     uint3 tid{0, 0, 0};
 };
@@ -74,6 +79,7 @@ struct Block {
     std::vector<Fiber> fibers;
     std::vector<WarpSlot> warps;
     ucontext_t sched;
+    jmp_buf sched_jb;
     int cur = -1;
     int bar_arrived = 0;
     int bar_gen = 0;
@@ -91,7 +97,7 @@ inline std::vector<unsigned char>& g_dyn() { static std::vector<unsigned char> v
 
 inline void yield() {
     Block* b = g_block();
-    swapcontext(&b->fibers[b->cur].ctx, &b->sched);
+    if (_setjmp(b->fibers[b->cur].jb) == 0) _longjmp(b->sched_jb, 1);
 }
 
 inline void block_barrier() {
@@ -146,7 +152,7 @@ inline void fiber_main() {
     Block* b = g_block();
     (*b->body)();
     b->fibers[b->cur].done = true;
-    swapcontext(&b->fibers[b->cur].ctx, &b->sched);
+    _longjmp(b->sched_jb, 1);
 }
 
 inline void run_block(const std::function<void()>& body, dim3 bd) {
@@ -160,10 +166,12 @@ inline void run_block(const std::function<void()>& body, dim3 bd) {
     g_block() = &blk;
     for (int t = 0; t < T; ++t) {
         Fiber& f = blk.fibers[t];
-        f.stack.resize(kStack);
+        static std::vector<unsigned char*> pool;
+        while ((int)pool.size() <= t) pool.push_back((unsigned char*)std::malloc(kStack));
+        f.stack = pool[t];
         f.tid = uint3{(unsigned)(t % bd.x), (unsigned)((t / bd.x) % bd.y), (unsigned)(t / (bd.x * bd.y))};
         getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = f.stack.data();
+        f.ctx.uc_stack.ss_sp = f.stack;
         f.ctx.uc_stack.ss_size = kStack;
         f.ctx.uc_link = &blk.sched;
         makecontext(&f.ctx, (void (*)())fiber_main, 0);
@@ -174,7 +182,11 @@ inline void run_block(const std::function<void()>& body, dim3 bd) {
         for (int t = 0; t < T; ++t) {
             if (blk.fibers[t].done) continue;
             blk.cur = t;
-            swapcontext(&blk.sched, &blk.fibers[t].ctx);
+            if (_setjmp(blk.sched_jb) == 0) {
+                Fiber& f = blk.fibers[t];
+                if (!f.started) { f.started = true; setcontext(&f.ctx); }
+                _longjmp(f.jb, 1);
+            }
             if (!blk.fibers[t].done) ++live;
         }
     }
