@@ -291,7 +291,7 @@ def test_row_features_warp_kernel(emu):
     assert np.array_equal(topv, np.sort(Cf, axis=1)[:, :16])
 
 
-@pytest.mark.parametrize("n,group,stream", [(512, 0, 0), (512, 0, 1), (1024, 2, 0)])       # other shapes: tests/test_gpu_round2.py
+@pytest.mark.parametrize("n,group,stream", [(512, 0, 0), (512, 0, 1), (1024, 2, 0), (2048, 4, 0)])       # other shapes: tests/test_gpu_round2.py
 def test_row_features_group_kernel(emu, n, group, stream):
     """The group kernel (features_group.cuh: G warps per row, sorted-sample brackets, lane-private byte histograms)
     with its redo hand-over to the CTA kernel, for one, two and four warps per row: uniform, 1e6-fill (count-only
@@ -337,7 +337,7 @@ def test_row_features_group_kernel(emu, n, group, stream):
         _opt(lib, ctx, "feat_group", 0)
         _opt(lib, ctx, "feat_stream", 0)
     print("rows handed to the fall-back kernel:", redo)
-    assert 0 <= redo <= 16, redo          # the adversarial rows may give up; the family rows must not
+    assert 1 <= redo <= 16, redo          # the adversarial rows give up (0 = the group kernel did not run); the family rows must not
     feature_close(feat[:rows], ref, rtol=1e-4)
     assert np.array_equal(topv[:rows], np.sort(Cf, axis=1)[:rows, :16])
 
@@ -347,10 +347,10 @@ def test_advanced_dual_sweeps(emu):
     NumPy statements, bit for bit, binary32- and binary64-stored matrices."""
     lib, ctx = emu
     rng = np.random.default_rng(21)
-    for n, f64 in ((20, False), (12, True)):                     # larger sizes on the GPU: tests/test_gpu_config_parity.py
+    for n, f64 in ((33, False), (24, True)):                     # larger sizes on the GPU: tests/test_gpu_config_parity.py
         C = gen.make_instance("uniform", n, seed=n) if not f64 else rng.uniform(0, 1, (n, n))
         u, v = noisy_oracle_seeds(C, 5e-2)
-        for rounds in (1, 4):
+        for rounds in (1, 12):
             ur, vr = u.copy(), v.copy()
             for _ in range(rounds):
                 ur = np.minimum(ur, (C - vr[None, :]).min(axis=1))
@@ -381,7 +381,7 @@ def test_oracle_duals_relaxation_matches_reference(emu):
     from solvers.dual_computation import finish_duals
     lib, ctx = emu
     g = _round2_golden()
-    for fam in ("sparse1e6", "metric", "clustered"):             # all five on the GPU: tests/test_gpu_round2.py
+    for fam in ("uniform", "sparse", "sparse1e6", "metric", "clustered"):
         C = np.ascontiguousarray(g[f"duals/{fam}/C"])
         n = C.shape[0]
         rows, cols = linear_sum_assignment(C)
@@ -414,7 +414,7 @@ def test_row_features_torch_mode(emu):
     g = _round2_golden()
     _opt(lib, ctx, "feat_torch_mode", 1)
     try:
-        for fam in ("sparse1e6", "metric", "clustered"):             # all five on the GPU: tests/test_gpu_round2.py
+        for fam in ("uniform", "sparse", "sparse1e6", "metric", "clustered"):
             C = np.ascontiguousarray(g[f"tfeat/{fam}/C"].astype(np.float32))
             n = C.shape[0]
             feat = np.zeros((n, 21), np.float32)
