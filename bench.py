@@ -223,23 +223,50 @@ def host_cores() -> int:
 
 # ---- clocks --------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons of GPU `index`, sampled during the timed region.  NVML in-process (nvidia_ml_py):
+    with one rank per GPU, eight ranks forking `nvidia-smi` five times a second contend for the driver's locks with
+    the kernel launches they are supposed to observe; the subprocess form is only the fall-back."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.th = threading.Thread(target=self.run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys))
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def sample(self):
+        if self.nvml is not None:
+            nv, h = self.nvml
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:  # noqa: BLE001
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            bits = (getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4))
+            return [str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for b in bits]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        return [c.strip() for c in out.split(",")] if out else None
 
     def run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
+                row = self.sample()
+                if row:
+                    self.rows.append(row)
+            except Exception:  # noqa: BLE001
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1 if self.nvml is not None else 0.5)
 
     def __enter__(self):
         self.th.start()
@@ -256,7 +283,7 @@ class ClockSampler:
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         reasons = [nm for k, nm in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---- the other BASELINE configs (rank 0, N=1): parity-test shapes, timed in the same run -------------------------
@@ -376,6 +403,8 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
     torch.cuda.set_device(local)
+    # one process per GPU: keep this rank's CPU threads and its pinned host buffers on the GPU's NUMA node
+    numa_node = b200lap.bind_to_device_numa_node(local) if world > 1 and os.environ.get("B200LAP_NO_NUMA_BIND", "0") != "1" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     ctx = b200lap.default_context(local)
@@ -454,7 +483,11 @@ def run_b200(args):
         out = step_resident()          # this rank's own batch, for the host-path comparison below
         ctx.sync()
     t = torch.tensor([ms_resident], dtype=torch.float64, device="cuda")
+    ms_by_rank = [round(ms_resident / args.steps, 3)]
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        ms_by_rank = [round(float(e.item()) / args.steps, 3) for e in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     tu = torch.tensor([float(units_done)], dtype=torch.float64, device="cuda")
@@ -604,9 +637,10 @@ def run_b200(args):
                                                    "mean_latency_s": round(float(np.mean(sper)), 3)}}
         line = {
             "metric": METRIC, "value": round(world * B / (ms_step * 1e-3), 2), "unit": "instances/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "ms_per_step_alone": round(ms_step_alone, 3), "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "ms_per_step_by_rank": ms_by_rank, "ms_per_step_alone": round(ms_step_alone, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": bench_config(world),
+            "numa_node_of_rank0": numa_node,
             "scheduling": ("dynamic: world x steps batch-units drained from one queue (b200lap.WorkQueue), units per rank " + str(units_per_rank))
                           if dynamic else "static: every rank steps over its own batch",
             "e2e": {"value": round(world * B / e2e_s, 2), "unit": "instances/s", "h2d_bytes_per_step": int(Ch.nbytes),

@@ -11,4 +11,4 @@ this package does not require a GPU, calling into it does.
 from ._lib import B200LapError, LIB_PATH, ROW_FEAT_DIM, TRACE_NAMES, load  # noqa: F401
 from .runtime import Context, HostPipeline, Model, default_context, pack_state_dict, state_dict_order, trace_dict  # noqa: F401
 from .predictor import GNNPredictor  # noqa: F401
-from .sharding import WorkQueue, drain_queue, shard_bounds, solve_sharded  # noqa: F401
+from .sharding import WorkQueue, bind_to_device_numa_node, drain_queue, shard_bounds, solve_sharded  # noqa: F401

@@ -100,3 +100,32 @@ def drain_queue(queue: "WorkQueue", launch: Callable[[int], "object"], in_flight
         wait(h)
         done.append(u)
     return done
+
+
+def bind_to_device_numa_node(device: int) -> Optional[int]:
+    """Restrict this process to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers allocated and
+    first-touched afterwards live in that node's memory: with one process per GPU and 2 GiB of binary64 matrices
+    uploaded per step, host->device copies that cross the socket interconnect are what limits the end-to-end rate of an
+    8-GPU box.  Returns the node, or None when the topology cannot be read (single node, containers without sysfs)."""
+    import os
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(device)
+        bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
