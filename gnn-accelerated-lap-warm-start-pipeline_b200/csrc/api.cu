@@ -341,7 +341,9 @@ int run_solve(b200lap_ctx* ctx, const CT* C, long long inst_stride, int ld, int 
                                      cluster > 1 ? kClusterSmemArrays : (1 << ST_COUNT) - 1);
     a.gws = nullptr; a.gws_stride = 0;
     if (a.smem_mask != (1 << ST_COUNT) - 1) {
-        const size_t stride = (state + 4096 + 255) & ~(size_t)255;
+        // (+ the per-scan column bitmaps of the cluster mode's batched relax step, at the tail of the stride)
+        const size_t cbm_bytes = (size_t)kMaxScans * ((((size_t)n + 31) / 32 + 4 + 3) & ~(size_t)3) * 4;
+        const size_t stride = (state + 4096 + cbm_bytes + 255) & ~(size_t)255;
         unsigned char* g = (unsigned char*)ctx->take(stride * (size_t)batch);
         if (!g) return fail(-1, "device workspace allocation failed (solver state)");
         a.gws = g; a.gws_stride = (long long)stride;

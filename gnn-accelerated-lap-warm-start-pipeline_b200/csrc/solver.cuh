@@ -62,6 +62,9 @@ struct SolverShared {
     int nh[3][kMaxScans];              // register-resident path: hits per scan
     HitResult res[2];                  // register-resident path: replay results, double-buffered by batch parity
     int box_op, box_row, box_js, box_hi, box_sp;   // cluster mode: the master's command mailbox, read by the workers through DSMEM
+    int box_k, box_rows[kMaxScans], box_jss[kMaxScans];   // cluster mode: the scans of one batched relax step (row, scanned column)
+    int bnhit[3][kMaxScans], bhit_j[3][kMaxScans];        // cluster mode: hits per scan and the first hit column published (3-slot rotation)
+    int bminw[3][kMaxScans], bmaxw[3][kMaxScans];         // cluster mode: word range of the scan's hits in its COLUMN bitmap
     unsigned int cursor, deferred;
     int hitk[64];           // positions of the flagged records of a collect step, ascending
     long long tr[kTraceWords];
@@ -186,6 +189,8 @@ template <typename CT> struct SolverCtx {
     int *minw, *maxw, *nhit, *hit_k, *hit_j;   // slot arrays: in SolverShared, or in the cluster mailbox (cluster mode)
     int nc, rank;                              // thread-block cluster size and this CTA's rank (1, 0 without a cluster)
     unsigned msh;                              // cluster mode: shared::cluster address of the MASTER's SolverShared
+    unsigned int* cbm;                         // cluster mode: per-scan COLUMN bitmaps of a batched relax step (global workspace)
+    int cbw;                                   // words per scan in cbm
     int regpath;                               // augmentation with register-resident d/v (solver_path.cuh)
     int kcap, pipe;
 };
@@ -422,6 +427,85 @@ __device__ __forceinline__ void relax_slice(SolverCtx<CT>& S, int i, int js, int
     }
 }
 
+// ---- cluster mode, batched: one CTA's slice of a relax step over up to kMaxScans SCAN columns at once.  The two cluster
+// barriers of a step (and the L2 round trips of pos / v / d) are paid once per batch instead of once per scanned column.
+// A thread relaxes its columns scan after scan in registers -- exactly the reference's sequential semantics per column
+// (lapjv.cpp:178-213): the distance a later scan compares with is the one the earlier scans left, and a column hit by
+// an earlier scan of the batch (cand == level: it moves to SCAN) is not touched by the later ones.  Hits are flagged per
+// scan in a bitmap indexed by COLUMN (positions move while the earlier scans of the batch are replayed); the master
+// turns every scan's column bits into position bits under the positions current at that moment and replays them in
+// ascending position order with the single-scan machinery.  If a scan ends the path, the later scans of the batch
+// never happened: their d / pred writes only touch TODO columns, which the next path re-initialises.
+template <typename CT>
+__device__ __forceinline__ void relax_slice_batch(SolverCtx<CT>& S, int K, const int* rows, const int* jss, int hi, int sp)
+{
+    const int n = S.n, T = blockDim.x, tid = threadIdx.x;
+    const int per = (n + S.nc - 1) / S.nc;
+    const int j0 = S.rank * per, j1 = min(n, j0 + per);
+    const double level = S.d[jss[0]];          // every SCAN column sits at the current level
+    const CT* crow[kMaxScans];
+    double slack[kMaxScans];
+#pragma unroll
+    for (int sc = 0; sc < kMaxScans; ++sc) {
+        const int r = sc < K ? rows[sc] : rows[0], js = sc < K ? jss[sc] : jss[0];
+        crow[sc] = S.C + (size_t)r * S.ld;
+        slack[sc] = ((double)__ldg(crow[sc] + js) - S.vg[js]) - level;
+    }
+    int wmin_i[kMaxScans], wmax_i[kMaxScans];
+#pragma unroll
+    for (int sc = 0; sc < kMaxScans; ++sc) { wmin_i[sc] = 0x7fffffff; wmax_i[sc] = -1; }
+    for (int base = j0 + tid; base < j1; base += 2 * T) {
+        CT cr[kMaxScans][2];
+        int kq[2];
+        double vq[2], dq[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = base + q * T;
+#pragma unroll
+            for (int sc = 0; sc < kMaxScans; ++sc) cr[sc][q] = (j < j1 && sc < K) ? __ldg(crow[sc] + j) : (CT)0;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = base + q * T;
+            kq[q] = j < j1 ? S.pos[j] : -1;
+            vq[q] = j < j1 ? S.vg[j] : 0.0;
+            dq[q] = j < j1 ? S.d[j] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = base + q * T;
+            if (kq[q] < hi) continue;
+            double dj = dq[q];
+            int pj = -1;
+#pragma unroll
+            for (int sc = 0; sc < kMaxScans; ++sc) {
+                if (sc >= K) break;
+                const double cand = ((double)cr[sc][q] - vq[q]) - slack[sc];
+                if (cand < dj) {
+                    dj = cand;
+                    pj = rows[sc];
+                    if (cand == level) {
+                        atomicOr(&S.cbm[(size_t)sc * S.cbw + (j >> 5)], 1u << (j & 31));
+                        wmin_i[sc] = min(wmin_i[sc], j >> 5);
+                        wmax_i[sc] = max(wmax_i[sc], j >> 5);
+                        if (dsm_add(S.msh + (unsigned)offsetof(SolverShared, bnhit) + 4u * (unsigned)(sp * kMaxScans + sc), 1) == 0)
+                            dsm_st(S.msh + (unsigned)offsetof(SolverShared, bhit_j) + 4u * (unsigned)(sp * kMaxScans + sc), j);
+                        break;                  // the column has left TODO for the later scans of the batch
+                    }
+                }
+            }
+            if (pj >= 0) { S.d[j] = dj; S.pred[j] = pj; }
+        }
+    }
+#pragma unroll
+    for (int sc = 0; sc < kMaxScans; ++sc) {
+        if (wmax_i[sc] >= 0) {
+            dsm_min(S.msh + (unsigned)offsetof(SolverShared, bminw) + 4u * (unsigned)(sp * kMaxScans + sc), wmin_i[sc]);
+            dsm_max(S.msh + (unsigned)offsetof(SolverShared, bmaxw) + 4u * (unsigned)(sp * kMaxScans + sc), wmax_i[sc]);
+        }
+    }
+}
+
 template <typename CT>
 __device__ void worker_loop(SolverCtx<CT>& S)
 {
@@ -429,11 +513,41 @@ __device__ void worker_loop(SolverCtx<CT>& S)
         cluster_sync_all();                                   // a command is posted
         const int op = dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_op));
         if (op == BOX_EXIT) { cluster_sync_all(); return; }   // the master's shared memory stays alive until everybody has read the command
-        const int row = dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_row)), js = dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_js));
+        const int K = dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_k));
         const int hi = dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_hi)), sp = dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_sp));
-        relax_slice(S, row, js, hi, sp);
+        int rows[kMaxScans], jss[kMaxScans];
+#pragma unroll
+        for (int sc = 0; sc < kMaxScans; ++sc) {
+            rows[sc] = sc < K ? dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_rows) + 4u * sc) : 0;
+            jss[sc] = sc < K ? dsm_ld(S.msh + (unsigned)offsetof(SolverShared, box_jss) + 4u * sc) : 0;
+        }
+        relax_slice_batch(S, K, rows, jss, hi, sp);
         cluster_sync_all();                                   // slices done, flags and d/pred visible
     }
+}
+
+// cluster mode: the hits of one scan of a batch, flagged by COLUMN, become position bits under the CURRENT positions
+// (warp 0; the words of the scan's range are cleared on the way).  Returns the position-word range through wlo / whi.
+template <typename CT>
+__device__ __forceinline__ void column_bits_to_positions(SolverCtx<CT>& S, int sc, int cw_lo, int cw_hi, int& wlo, int& whi)
+{
+    const int lane = lane_id();
+    int mn = 0x7fffffff, mx = -1;
+    unsigned int* cb = S.cbm + (size_t)sc * S.cbw;
+    for (int w0 = cw_lo; w0 <= cw_hi; w0 += 32) {
+        unsigned int bits = 0;
+        if (w0 + lane <= cw_hi) { bits = cb[w0 + lane]; if (bits) cb[w0 + lane] = 0u; }
+        while (bits) {
+            const int bpos = __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            const int k = S.pos[(w0 + lane) * 32 + bpos];
+            atomicOr(&S.bitmap[k >> 5], 1u << (k & 31));
+            mn = min(mn, k >> 5); mx = max(mx, k >> 5);
+        }
+    }
+    __syncwarp();
+    wlo = __reduce_min_sync(kFull, mn);
+    whi = __reduce_max_sync(kFull, mx);
 }
 
 }  // namespace b200lap
@@ -454,6 +568,8 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
         S.d[j] = c - S.v[j];
         if (S.vg != S.v) S.vg[j] = S.v[j];     // cluster mode: the workers' copy of v for this path
     });
+    if (S.nc > 1)                              // cluster mode: scans discarded when the previous path ended may have left column bits
+        for (int w = tid; w < kMaxScans * S.cbw; w += T) S.cbm[w] = 0u;
     __syncthreads();
     int lo = 0, hi = 0, n_ready = 0, final_j = -1;
     while (final_j < 0) {
@@ -535,6 +651,57 @@ __device__ int shortest_path(SolverCtx<CT>& S, int start_i)
         // ---- relax from every SCAN column in turn (_scan_dense)
         const long long tr0 = sm_clock();
         while (final_j < 0 && lo != hi) {
+            if (S.nc > 1) {
+                // ---- cluster mode: up to kcap SCAN columns per step (relax_slice_batch), replayed scan by scan
+                const int sp = S.step % 3;
+                const int K = min(min(S.kcap, kMaxScans), hi - lo);
+                if (tid < K) { const int js = S.cols[lo + tid]; sh->box_jss[tid] = js; sh->box_rows[tid] = S.y[js]; }
+                if (tid == 0) { sh->box_op = BOX_RELAX; sh->box_k = K; sh->box_hi = hi; sh->box_sp = sp; }
+                cluster_sync_all();
+                relax_slice_batch(S, K, sh->box_rows, sh->box_jss, hi, sp);
+                cluster_sync_all();
+                S.step++;
+                int consumed = 0;
+                for (int sc = 0; sc < K && final_j < 0; ++sc) {
+                    ++consumed;
+                    const int nh = sh->bnhit[sp][sc];
+                    if (nh == 0) continue;
+                    if (nh == 1) {
+                        if (tid == 0) {
+                            const int j = sh->bhit_j[sp][sc];
+                            S.cbm[(size_t)sc * S.cbw + (j >> 5)] = 0u;       // its only bit in that word range
+                            const int k = S.pos[j];
+                            int fin = -1, nhi = hi;
+                            if (S.y[j] < 0) {
+                                fin = j;
+                            } else {
+                                const int c2 = S.cols[hi];
+                                S.cols[k] = c2; S.pos[c2] = k;
+                                S.cols[hi] = j; S.pos[j] = hi;
+                                nhi = hi + 1;
+                            }
+                            sh->hi = nhi; sh->final_j = fin;
+                            B200LAP_PROF(sh->tr[TR_RELAX_HITS] += 1);
+                        }
+                    } else if (warp_id() == 0) {
+                        int wlo, whi;
+                        column_bits_to_positions(S, sc, sh->bminw[sp][sc], sh->bmaxw[sp][sc], wlo, whi);
+                        replay_relax(S, hi, wlo, whi);
+                    }
+                    __syncthreads();
+                    hi = sh->hi;
+                    final_j = sh->final_j;
+                }
+                lo += consumed;
+                // the slot is reset right after its use (collect steps advance the slot rotation too, but know nothing of the
+                // per-scan arrays); the workers write it again only behind the next step's first cluster barrier
+                __syncthreads();
+                if (tid == 0) {
+                    for (int sc = 0; sc < kMaxScans; ++sc) { sh->bnhit[sp][sc] = 0; sh->bminw[sp][sc] = 0x7fffffff; sh->bmaxw[sp][sc] = -1; }
+                    sh->tr[TR_RELAX] += consumed;
+                }
+                continue;
+            }
             const int js = S.cols[lo];
             const int i = S.y[js];
             const bool solo = S.nc == 1;             // cluster mode: every CTA fetches these three itself (relax_slice)
@@ -874,6 +1041,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     S.nc = a.cluster > 1 ? a.cluster : 1;
     S.rank = a.cluster > 1 ? (int)(blockIdx.x % (unsigned)a.cluster) : 0;
     S.msh = S.nc > 1 ? dsm_map(&sh, 0u) : 0u;
+    // cluster mode: the per-scan column bitmaps of the batched relax step sit at the tail of the instance's workspace stride
+    S.cbw = ((n + 31) / 32 + 4 + 3) & ~3;
+    S.cbm = (S.nc > 1 && a.gws) ? (unsigned int*)(a.gws + (size_t)(b + 1) * a.gws_stride) - (size_t)kMaxScans * S.cbw : nullptr;
     S.regpath = (a.regpath && S.nc == 1 && a.smem_mask == (1 << ST_COUNT) - 1) ? 1 : 0;
     S.kcap = a.kcap > 0 ? a.kcap : kMaxScans;
     S.pipe = a.pipe;
@@ -881,7 +1051,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_solve(SolveArgs<CT> a)
     if (S.rank != 0) { worker_loop(S); return; }
     if (tid == 0) {
         sh.s_cnt = 0;
-        for (int q = 0; q < 3; ++q) { S.minw[q] = 0x7fffffff; S.nhit[q] = 0; S.maxw[q] = -1; for (int s2 = 0; s2 < kMaxScans; ++s2) sh.nh[q][s2] = 0; }
+        for (int q = 0; q < 3; ++q) {
+            S.minw[q] = 0x7fffffff; S.nhit[q] = 0; S.maxw[q] = -1;
+            for (int s2 = 0; s2 < kMaxScans; ++s2) { sh.nh[q][s2] = 0; sh.bnhit[q][s2] = 0; sh.bminw[q][s2] = 0x7fffffff; sh.bmaxw[q][s2] = -1; }
+        }
         for (int q = 0; q < kTraceWords; ++q) sh.tr[q] = 0;
     }
     for (int w = tid; w < (n + 31) / 32 + 4; w += T) S.bitmap[w] = 0u;

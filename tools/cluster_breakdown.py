@@ -12,7 +12,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 g = torch.Generator(device="cuda").manual_seed(42)
 Cd = torch.rand((1, n, n), generator=g, device="cuda", dtype=torch.float32)
 u64, v64, _ = ctx.predict_duals(model, Cd)
-for nc in (8, 1):
+for nc in (8,):
     ctx.set_option("solver_cluster", nc)
     out = ctx.solve_seeded(Cd, u64, v64, want_trace=True); ctx.sync()
     t = out[3].cpu().numpy()[0]
