@@ -25,6 +25,7 @@ data-path collective); the timed region is bracketed by barrier + synchronize, t
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -445,6 +446,9 @@ def run_b200(args):
             dist.broadcast(t, src=b)
             batches.append(t)
         torch.cuda.synchronize()
+    # every lane gets at least one untimed step: a lane's first call allocates its workspace (cudaMalloc synchronises the
+    # device), which otherwise lands inside the timed region as a 29 -> 36-45 ms step (tools/lane_jitter.py)
+    args.warmup = max(args.warmup, LANES)
     for _ in range(args.warmup):
         out = step_resident()
     ctx.sync()
@@ -574,6 +578,16 @@ def run_b200(args):
     #    b200lap_pipeline_batch_submit / _wait; every step uploads its 2 GiB of binary64 matrices and downloads its
     #    assignments inside the timed region, the upload of step k+1 overlaps the solve of step k
     torch.cuda.set_device(local)          # the host entry points use the library's default context: make it this rank's device
+    # host-side marshalling of the upload (csrc/host_narrow.cpp): threads per rank scaled to the ranks sharing the host
+    lws = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+    # measured (profiles/r02_host_narrow_sweep.txt): one rank gains 35 % from narrowing 70 % of the batch on 12 host threads; the
+    # host cores narrow at most ~85 GB/s in total, so with two ranks the gain is 3 % (50 % on 8 threads each) and beyond
+    # that the plain binary64 DMA is kept
+    hn_threads, hn_percent = {1: (12, 70), 2: (8, 50)}.get(lws, (1, 0))
+    os.environ.setdefault("B200LAP_HOST_NARROW_THREADS", str(max(1, min(hn_threads, host_cores() // lws))))
+    os.environ.setdefault("B200LAP_HOST_NARROW_PERCENT", str(hn_percent))
+    hn_t, hn_p = ctypes.c_int(0), ctypes.c_int(0)
+    h2d_bytes = int(ctx.lib.b200lap_host_narrow_config(B, n, ctypes.byref(hn_t), ctypes.byref(hn_p)))
     hp = b200lap.HostPipeline(named_state_dict(), topk=16, lanes=LANES)
     hbuf = [(torch.empty((B, n), dtype=torch.int64).pin_memory(), torch.empty((B, n), dtype=torch.int64).pin_memory(),
              np.zeros(B, dtype=np.int32)) for _ in range(LANES)]
@@ -643,8 +657,11 @@ def run_b200(args):
             "numa_node_of_rank0": numa_node,
             "scheduling": ("dynamic: world x steps batch-units drained from one queue (b200lap.WorkQueue), units per rank " + str(units_per_rank))
                           if dynamic else "static: every rank steps over its own batch",
-            "e2e": {"value": round(world * B / e2e_s, 2), "unit": "instances/s", "h2d_bytes_per_step": int(Ch.nbytes),
+            "e2e": {"value": round(world * B / e2e_s, 2), "unit": "instances/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(B * n * 8 * 2 + rch.nbytes + 4), "steps": e2e_steps,
+                    "host_input_bytes_per_step": int(Ch.nbytes),
+                    "upload": f"first {hn_p.value}% of the instances narrowed to binary32 by {hn_t.value} host threads (exactness-checked), the rest "
+                              "uploaded as binary64 by DMA meanwhile and narrowed on the device",
                     "api": f"b200lap_pipeline_batch_submit/_wait, {LANES} batches in flight",
                     "one_batch_at_a_time": {"value": round(world * B / e2e_sync_s, 2), "unit": "instances/s", "api": "b200lap_pipeline_batch"}},
             "gpu_launches": int(launches),

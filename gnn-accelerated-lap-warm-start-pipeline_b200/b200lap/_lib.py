@@ -68,6 +68,7 @@ SIGNATURES = {
     "b200lap_ctx_join": (ctypes.c_int, [vp]),
     "b200lap_pipeline_batch_submit": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp, vp, ctypes.POINTER(vp)]),
     "b200lap_pipeline_batch_wait": (ctypes.c_int, [vp]),
+    "b200lap_host_narrow_config": (ctypes.c_longlong, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "b200lap_default_ctx": (vp, []),
 }
 

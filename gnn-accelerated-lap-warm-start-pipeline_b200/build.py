@@ -37,7 +37,7 @@ def nvcc_path() -> str:
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.cpp")) +
                   glob.glob(os.path.join(CSRC, "*.inc")) + [os.path.join(HERE, "..", "include", "b200lap.h")])
 
 
@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False, profile: bool = False) -> 
     if os.environ.get("B200LAP_KMAX"):       # experiment builds (tools/): scans per batched relax step
         prof += ["-DB200LAP_KMAX=" + os.environ["B200LAP_KMAX"]]
         out = out.replace(".so", "_k" + os.environ["B200LAP_KMAX"] + ".so")
-    cmd = [nvcc_path()] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(CSRC, "api.cu")]
+    cmd = [nvcc_path()] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(CSRC, "api.cu"), os.path.join(CSRC, "host_narrow.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

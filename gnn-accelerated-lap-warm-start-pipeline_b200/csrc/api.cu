@@ -25,6 +25,13 @@
 #include "mlp_tc.cuh"
 #include "../../include/b200lap.h"
 
+// host_narrow.cpp: binary64 -> binary32 marshalling of host buffers (multi-threaded, exactness-checked)
+namespace b200lap_host {
+int narrow_threads();
+int narrow_percent();
+bool narrow(const double* src, float* dst, size_t count, int threads);
+}
+
 using namespace b200lap;
 
 // ---------------------------------------------------------------------------------------------

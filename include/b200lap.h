@@ -59,11 +59,12 @@ int b200lap_lapjv_seeded_batch(const double* C, int batch, int n, long long* x, 
 int b200lap_ctx_create(int device, void* stream, b200lap_ctx** out);
 void b200lap_ctx_destroy(b200lap_ctx* ctx);
 void* b200lap_ctx_stream(b200lap_ctx* ctx);          /* the cudaStream_t work is enqueued on */
-int b200lap_ctx_sync(b200lap_ctx* ctx);               /* waits for both lanes */
-/* A context has two LANES (stream + workspace each).  With the option overlap_steps = 1, consecutive
- * b200lap_dev_pipeline calls alternate between them, so two independent batches are in flight (a 64-instance solve
- * occupies 64 of the 148 SMs).  Results of such calls are complete after b200lap_ctx_sync, or -- for work enqueued on
- * lane 0's stream -- after b200lap_ctx_join, which makes lane 0's stream wait for lane 1 on the device. */
+int b200lap_ctx_sync(b200lap_ctx* ctx);               /* waits for every lane */
+/* A context has up to eight LANES (stream + workspace each).  With the option overlap_steps = L (2..8), consecutive
+ * b200lap_dev_pipeline calls rotate over L of them, so L independent batches are in flight (a 64-instance solve
+ * occupies 64 of the 148 SMs; overlap_steps < 2 = one batch at a time).  Results of such calls are complete after
+ * b200lap_ctx_sync, or -- for work enqueued on lane 0's stream -- after b200lap_ctx_join, which makes lane 0's stream
+ * wait for the other lanes on the device.  A lane's first call allocates its workspace: warm every lane before timing. */
 void* b200lap_ctx_lane_stream(b200lap_ctx* ctx, int lane);
 int b200lap_ctx_last_lane(b200lap_ctx* ctx);            /* lane the most recent b200lap_dev_pipeline call was enqueued on */
 int b200lap_ctx_join(b200lap_ctx* ctx);
@@ -170,12 +171,20 @@ int b200lap_project_feasible(const double* C, int n, double* u, double* v, int m
 int b200lap_reduce_costs(const double* C, int n, const double* u, const double* v, int shift_nonneg, double* out,
                          double* min_out);
 /* Asynchronous form of b200lap_pipeline_batch for throughput: submit() enqueues upload, pipeline and download on one of
- * the default context's two lanes and returns at once (pass pinned host memory for C, or the upload blocks); wait()
- * blocks until that batch is complete, writes x, y [batch][n] (rows of instances with rc != 0 read -1) and rc, and
- * frees the job.  At most two batches may be outstanding (one per lane): submit k+2 needs wait k first. */
+ * the default context's lanes (option overlap_steps = 2..8 through b200lap_ctx_set_option, at least two here) and returns once the host-side
+ * marshalling of the upload is done (pass pinned host memory for C, or the upload blocks); wait() blocks until that
+ * batch is complete, writes x, y [batch][n] (rows of instances with rc != 0 read -1) and rc, and frees the job.  One
+ * batch may be outstanding per lane: with L lanes, submit k+L needs wait k first. */
 int b200lap_pipeline_batch_submit(const b200lap_model* model, const double* C, int batch, int n, double eps, long long* x,
                                   long long* y, int* rc, b200lap_job** job);
 int b200lap_pipeline_batch_wait(b200lap_job* job);
+/* How submit() moves a batch to the device: the first `head` = round(batch * percent / 100) instances are narrowed to
+ * binary32 by `threads` host threads into pinned staging and uploaded at 4 bytes per entry, while the remaining
+ * instances go up as binary64 by DMA and are narrowed on the device (csrc/host_narrow.cpp; the reference hands over
+ * binary64 matrices, scripts/gnn_benchmark.py:226).  B200LAP_HOST_NARROW_THREADS (0 = everything as binary64) and
+ * B200LAP_HOST_NARROW_PERCENT set them; a head that is not binary32-representable is uploaded as binary64 too.
+ * Returns the bytes submit() copies host -> device for a representable (batch, n) batch. */
+long long b200lap_host_narrow_config(int batch, int n, int* threads, int* percent);
 b200lap_ctx* b200lap_default_ctx(void);
 
 #ifdef __cplusplus

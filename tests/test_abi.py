@@ -84,3 +84,32 @@ def test_python_binding_argument_checks():
         lap.lapjv(np.zeros((2, 3)))
     with pytest.raises(ValueError):
         lap.lapjv(np.zeros(3))
+
+
+def test_host_narrowing_of_the_upload(built_lib):
+    """csrc/host_narrow.cpp marshals the host buffers of b200lap_pipeline_batch_submit (binary64 -> binary32 with an
+    exactness check; the reference hands over binary64 matrices, scripts/gnn_benchmark.py:226).  Host-only code: checked
+    here against numpy's own narrowing, including the cases that must be refused."""
+    narrow = getattr(built_lib, "_ZN12b200lap_host6narrowEPKdPfmi")
+    narrow.restype = ctypes.c_bool
+    narrow.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    rng = np.random.default_rng(0)
+    for count in (1, 7, 8, 9, 1000, (1 << 20) + 3):
+        a = rng.uniform(0, 1, count).astype(np.float32).astype(np.float64)
+        for threads in (1, 3, 8):
+            out = np.full(count, -1.0, np.float32)
+            assert narrow(a.ctypes.data, out.ctypes.data, count, threads)
+            assert np.array_equal(out, a.astype(np.float32)), (count, threads)
+        out = np.empty(count, np.float32)
+        b = a.copy(); b[count // 2] = 0.1            # not binary32-representable
+        assert not narrow(b.ctypes.data, out.ctypes.data, count, 4)
+        c = a.copy(); c[-1] = np.nan                 # NaN never survives the round-trip comparison
+        assert not narrow(c.ctypes.data, out.ctypes.data, count, 4)
+        d = a.copy(); d[0] = 1e300                   # overflows binary32
+        assert not narrow(d.ctypes.data, out.ctypes.data, count, 2)
+    t, p = ctypes.c_int(-1), ctypes.c_int(-1)
+    built_lib.b200lap_host_narrow_config.restype = ctypes.c_longlong
+    nbytes = built_lib.b200lap_host_narrow_config(64, 2048, ctypes.byref(t), ctypes.byref(p))
+    assert t.value >= 0 and 0 <= p.value <= 100
+    head = (64 * p.value + 50) // 100 if t.value > 0 else 0
+    assert nbytes == 2048 * 2048 * (head * 4 + (64 - head) * 8)
