@@ -929,12 +929,64 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
         Top2 tf;            // filtered set
         top2_init(tf);
         int f = 0x7fffffff;
-        row_scan<MAXC>(crow, n, [&](int j, double c) {
-            if (j != 0) {
-                const double red = c - S.v[j];
-                if (red < B200LAP_LARGE) { top2_push_inc(tf, red, j); f = min(f, j); }
+        if constexpr (MAXC > 0) {
+            // The lexicographic (value, index) top-2 of the thread's entries by a TOURNAMENT instead of a running update:
+            // the running form (generic branch below) carries a1 / a2 from entry to entry -- ncu of the cold n = 4096 solve
+            // (profiles/r02_ncu_cold_solve_4096.txt) shows 33 instructions and ~100 cycles per entry with the v[j] load and
+            // its dependent DADD inside each entry's branch.  Here every load and every subtraction is independent, a
+            // filtered entry becomes the empty slot (+inf, INT_MAX), and log2(MAXC) levels of merges follow.  Entries are in
+            // increasing column order and a merge prefers its left operand on ties, so the result is the same pair.
+            double ra[MAXC];
+            int ri[MAXC];
+#pragma unroll
+            for (int q = 0; q < MAXC; ++q) {
+                const int j = tid + q * T;
+                ra[q] = j < n ? (double)__ldg(crow + j) : INFINITY;
             }
-        });
+#pragma unroll
+            for (int q = 0; q < MAXC; ++q) {
+                const int j = tid + q * T;
+                const double red = ra[q] - (j < n ? S.v[j] : 0.0);
+                const bool ok = j < n && j != 0 && red < B200LAP_LARGE;
+                ra[q] = ok ? red : INFINITY;
+                ri[q] = ok ? j : 0x7fffffff;
+                f = ok ? min(f, j) : f;
+            }
+            Top2 tt[(MAXC + 1) / 2];
+#pragma unroll
+            for (int q = 0; q < MAXC; q += 2) {
+                Top2& o = tt[q / 2];
+                if (q + 1 < MAXC) {
+                    const bool p = ra[q + 1] < ra[q];
+                    o.a1 = p ? ra[q + 1] : ra[q]; o.i1 = p ? ri[q + 1] : ri[q];
+                    o.a2 = p ? ra[q] : ra[q + 1]; o.i2 = p ? ri[q] : ri[q + 1];
+                } else {
+                    o.a1 = ra[q]; o.i1 = ri[q]; o.a2 = INFINITY; o.i2 = 0x7fffffff;
+                }
+            }
+#pragma unroll
+            for (int w = 1; w < (MAXC + 1) / 2; w *= 2) {
+#pragma unroll
+                for (int q = 0; q + w < (MAXC + 1) / 2; q += 2 * w) {
+                    Top2& A = tt[q];
+                    const Top2 B = tt[q + w];
+                    const bool p = B.a1 < A.a1;                      // the right operand wins only when strictly smaller
+                    const double xa = p ? A.a1 : A.a2; const int xi = p ? A.i1 : A.i2;
+                    const double ya = p ? B.a2 : B.a1; const int yi = p ? B.i2 : B.i1;
+                    const bool s2 = ya < xa;
+                    A.a1 = p ? B.a1 : A.a1; A.i1 = p ? B.i1 : A.i1;
+                    A.a2 = s2 ? ya : xa;    A.i2 = s2 ? yi : xi;
+                }
+            }
+            tf = tt[0];
+        } else {
+            row_scan<MAXC>(crow, n, [&](int j, double c) {
+                if (j != 0) {
+                    const double red = c - S.v[j];
+                    if (red < B200LAP_LARGE) { top2_push_inc(tf, red, j); f = min(f, j); }
+                }
+            });
+        }
         if (c0 < B200LAP_LARGE) {
             if (tid == 0) top2_push(tf, c0, 0);
             t = block_top2(S.R, tf);
