@@ -929,7 +929,9 @@ __device__ int arr_pass(SolverCtx<CT>& S, int n_free)
         Top2 tf;            // filtered set
         top2_init(tf);
         int f = 0x7fffffff;
-        if constexpr (MAXC > 0) {
+        if constexpr (MAXC >= 16) {
+            // (measured: 8 x 8192 cold fallback 5464 -> 5042 ms with 16 entries per thread; with 8 entries per thread the
+            // running form is 6 % faster, so shorter rows keep it)
             // The lexicographic (value, index) top-2 of the thread's entries by a TOURNAMENT instead of a running update:
             // the running form (generic branch below) carries a1 / a2 from entry to entry -- ncu of the cold n = 4096 solve
             // (profiles/r02_ncu_cold_solve_4096.txt) shows 33 instructions and ~100 cycles per entry with the v[j] load and
