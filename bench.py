@@ -631,7 +631,7 @@ def run_b200(args):
         fk = dense["row_features"]
         achieved = fk["GBps_one_read_of_C"]
         cpu = None
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:      # the CPU sample is timed on rank 0 at N = 1 only
             procs = host_cores()
             sample = min(B, max(procs, 32))
             arm = CpuArm(Ch[:sample], procs)
@@ -660,8 +660,9 @@ def run_b200(args):
             "e2e": {"value": round(world * B / e2e_s, 2), "unit": "instances/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": int(B * n * 8 * 2 + rch.nbytes + 4), "steps": e2e_steps,
                     "host_input_bytes_per_step": int(Ch.nbytes),
-                    "upload": f"first {hn_p.value}% of the instances narrowed to binary32 by {hn_t.value} host threads (exactness-checked), the rest "
-                              "uploaded as binary64 by DMA meanwhile and narrowed on the device",
+                    "upload": (f"first {hn_p.value}% of the instances narrowed to binary32 by {hn_t.value} host threads (exactness-checked), the rest "
+                               "uploaded as binary64 by DMA meanwhile and narrowed on the device") if hn_p.value > 0 and hn_t.value > 0 else
+                              "whole batch uploaded as binary64 by DMA and narrowed on the device (several ranks share this host's cores and memory)",
                     "api": f"b200lap_pipeline_batch_submit/_wait, {LANES} batches in flight",
                     "one_batch_at_a_time": {"value": round(world * B / e2e_sync_s, 2), "unit": "instances/s", "api": "b200lap_pipeline_batch"}},
             "gpu_launches": int(launches),
