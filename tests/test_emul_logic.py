@@ -104,6 +104,28 @@ def test_solver_ties_and_known_answers(emu):
     _opt(lib, ctx, "solver_threads", 0)
 
 
+def test_cold_solve_with_sixteen_entries_per_thread(emu):
+    """Rows with 9..16 entries per thread take the tournament form of the ARR row scan (solver.cuh: arr_pass, the shape
+    of n = 8192 / 16384 on the GPU): lexicographic (value, column) top-2 with ties, entries >= LARGE filtered out and a
+    ragged last entry, against the port of lapjv.cpp:76-149."""
+    lib, ctx = emu
+    _opt(lib, ctx, "solver_threads", 32)
+    cases = [("uniform", gen.make_instance("uniform", 293, seed=5)),
+             ("sparse1e6", gen.make_instance("sparse1e6", 300, seed=6)),
+             ("clustered", gen.make_instance("clustered", 512, seed=7)),
+             ("int-ties", dense_int(330, 6, True, seed=8).astype(np.float64)),
+             ("int-ties-easy", dense_int(289, 4, False, seed=9).astype(np.float64))]
+    for name, C in cases:
+        rc, x, y = _capi.cold(lib, C)
+        xo, yo = oracle.port_lapjv_internal(C)
+        assert rc == 0 and np.array_equal(x, xo) and np.array_equal(y, yo), name
+    # the seeded entry's cold fallback goes through the same pass
+    C = cases[0][1]
+    u, v = noisy_oracle_seeds(C, 1e-2)
+    _check_seeded(lib, C, u, v, ("uniform", 293, "noisy"))
+    _opt(lib, ctx, "solver_threads", 0)
+
+
 def test_solver_mixed_state_placement(emu):
     """Large instances keep only the hottest state arrays (d, pos, v, ...) in shared memory and the rest in the
     global workspace; a tiny shared budget forces the same split on a small instance."""
