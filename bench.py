@@ -581,9 +581,9 @@ def run_b200(args):
     # host-side marshalling of the upload (csrc/host_narrow.cpp): threads per rank scaled to the ranks sharing the host
     lws = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
     # measured (profiles/r02_host_narrow_sweep.txt): one rank gains 35 % from narrowing 70 % of the batch on 12 host threads; the
-    # host cores narrow at most ~85 GB/s in total, so with two ranks the gain is 3 % (50 % on 8 threads each) and beyond
-    # that the plain binary64 DMA is kept
-    hn_threads, hn_percent = {1: (12, 70), 2: (8, 50)}.get(lws, (1, 0))
+    # box's 16 cores narrow at most ~85 GB/s in total, so the share shrinks with the ranks per host: +3 % at two ranks (50 % on 8
+    # threads each), +9 % at four (50 % on 4), and at eight the plain binary64 DMA wins (5258 vs 4342 inst/s with 30 % on 2)
+    hn_threads, hn_percent = {1: (12, 70), 2: (8, 50), 4: (4, 50)}.get(lws, (1, 0))
     os.environ.setdefault("B200LAP_HOST_NARROW_THREADS", str(max(1, min(hn_threads, host_cores() // lws))))
     os.environ.setdefault("B200LAP_HOST_NARROW_PERCENT", str(hn_percent))
     hn_t, hn_p = ctypes.c_int(0), ctypes.c_int(0)
@@ -707,7 +707,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "instances/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1e3 * sum(walls) / len(walls), 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": bench_config(1),
+            "config": bench_config(world),          # the B200 arm's config key for key (the driver compares them); the CPU work is the same at every N
             "cpu_baseline": {"value": round(v, 3), "unit": "instances/s", "cores": procs, "kind": arm.kind,
                              "sample": f"each step = the {BATCH} mixed-family n={N_INST} instances of rank 0's batch over {procs} worker processes, 1 thread each",
                              "pipeline": "reference's own gnn.compute_row_features + torch-CPU OneGNN + lap.lapjv_seeded (oracle/_ref/pyref)"
