@@ -305,6 +305,15 @@ class Context:
                     st.wait_stream(cur)
             check(self.lib.b200lap_dev_pipeline(self.handle, model.handle, ptr(C), f64, B, n, float(eps), ptr(x), ptr(y), ptr(rc), ptr(u64), ptr(v64), ptr(tr)),
                   "b200lap_dev_pipeline", self.lib)
+            if overlap:
+                # The tensors were allocated on torch's current stream but are written (u64 / v64 also read back) by the lane's
+                # kernels, which may still be queued when the caller drops them: without this torch's caching allocator hands
+                # the memory to the next call at once, and a later batch's duals can land in a block an earlier lane's solve
+                # is about to write its assignment into (seen once as "the lanes disagree" and as a 34 ms step at N = 2).
+                used = self.lane_stream(int(self.lib.b200lap_ctx_last_lane(self.handle)))
+                for t in (x, y, rc, u64, v64, tr):
+                    if t is not None:
+                        t.record_stream(used)
         if not overlap and cur.cuda_stream != lanes[0].cuda_stream:
             cur.wait_stream(lanes[0])
         return (x, y, rc, u64, v64, tr) if want_trace else (x, y, rc, u64, v64)
