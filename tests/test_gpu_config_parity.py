@@ -232,3 +232,33 @@ def test_advanced_dual_dropins(fam):
             assert raw.min() < 0 and np.array_equal(R, raw - raw.min())
             assert np.array_equal(ad.reduce_costs(C, u, v, shift_nonneg=False), raw)
             assert np.array_equal(ad.reduce_costs(C, up, vp), red if red.min() >= 0 else red - red.min())
+
+
+def test_batches_in_flight_on_every_lane_agree_with_one_at_a_time(ctx, model):
+    """Context.set_overlap(L): whole-pipeline calls rotate over L lanes.  Every call must return what the
+    same call returns alone -- also when the caller drops results while later lanes are still queued (the returned
+    tensors carry the lane's stream, so torch's allocator cannot recycle them under a running lane)."""
+    import torch
+    fams = ("uniform", "sparse", "metric", "clustered")
+    n, B = 512, 16
+    C = torch.from_numpy(np.stack([gen.make_instance(fams[k % 4], n, seed=900 + k) for k in range(B)]).astype(np.float32)).cuda()
+    ctx.set_overlap(False)
+    x0, y0, rc0, u0, v0 = ctx.pipeline(model, C)
+    ctx.sync()
+    assert (rc0.cpu().numpy() == 0).all()
+    x0, y0, u0, v0 = x0.clone(), y0.clone(), u0.clone(), v0.clone()
+    for lanes in (2, 8):
+        ctx.set_overlap(lanes)
+        try:
+            kept = []
+            for step in range(3 * lanes):
+                out = ctx.pipeline(model, C)
+                kept.append(out if step % 3 == 0 else (out[0], out[1]))      # most calls drop rc / u / v at once
+                del out
+            ctx.sync()
+            for k, o in enumerate(kept):
+                assert torch.equal(o[0], x0) and torch.equal(o[1], y0), (lanes, k)
+                if len(o) > 2:
+                    assert (o[2].cpu().numpy() == 0).all() and torch.equal(o[3], u0) and torch.equal(o[4], v0), (lanes, k)
+        finally:
+            ctx.set_overlap(False)
